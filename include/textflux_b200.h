@@ -1,0 +1,114 @@
+/* textflux_b200 C ABI: the drop-in boundary for the TextFlux / FLUX-Fill denoising hot path on B200 (sm_100a).
+ *
+ * The reference has no native code and no FFI; the boundary it exposes for this path is two Python calls inside
+ * FluxFillPipeline.__call__ (reference: diffusers/src/diffusers/pipelines/flux/pipeline_flux_fill.py):
+ *     :2084-2094   noise_pred = self.transformer(hidden_states=..., timestep=..., guidance=..., ...)[0]
+ *     :2098        latents    = self.scheduler.step(noise_pred, t, latents, return_dict=False)[0]
+ * Each entry point below names the reference interface it replaces.  Plain pointers and sizes only; every device
+ * pointer is bf16 unless stated; `stream` is a cudaStream_t passed as void*.  All functions return 0 on success and a
+ * non-zero tfx_status otherwise (never throw); tfx_last_error() gives the message.  A handle is bound to one device
+ * and is not re-entrant (the reference is single-threaded per process, one stream).
+ */
+#ifndef TEXTFLUX_B200_H_
+#define TEXTFLUX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tfx_model* tfx_handle;
+
+typedef enum {
+  TFX_OK = 0,
+  TFX_ERR_INVALID = 1, /* bad argument / unsupported shape (the reference raises ValueError) */
+  TFX_ERR_STATE = 2,   /* call order violated (weights not finalized, prepare() missing) */
+  TFX_ERR_CUDA = 3,    /* CUDA runtime / driver failure */
+  TFX_ERR_MISSING = 4  /* a weight the config requires was never set */
+} tfx_status;
+
+/* Mirrors FluxTransformer2DModel.__init__'s @register_to_config arguments
+ * (models/transformers/transformer_flux.py:865-879). */
+typedef struct {
+  int32_t in_channels;
+  int32_t out_channels;
+  int32_t num_layers;
+  int32_t num_single_layers;
+  int32_t attention_head_dim;
+  int32_t num_attention_heads;
+  int32_t joint_attention_dim;
+  int32_t pooled_projection_dim;
+  int32_t guidance_embeds;
+  int32_t axes_dims_rope[3];
+} tfx_config;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------------- */
+/* replaces FluxTransformer2DModel.__init__ (transformer_flux.py:865-921) */
+int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
+void tfx_destroy(tfx_handle h);
+/* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
+const char* tfx_last_error(tfx_handle h);
+/* "gemm_cta_group" (1|2), "attn_q_tiles" (1|2), "use_graph" (0|1) */
+int tfx_set_option(tfx_handle h, const char* key, int64_t value);
+/* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step */
+int tfx_get_counter(tfx_handle h, const char* key, int64_t* value);
+
+/* ---- weights (replaces load_state_dict on the reference module; names listed in INTEGRATION.md) -------------- */
+/* Registers a bf16 device tensor [rows, cols] (row-major, 16-byte aligned) under a packed-layout name.
+ * The caller keeps the memory alive for the handle's lifetime. */
+int tfx_set_weight(tfx_handle h, const char* name, const void* dev_ptr, int64_t rows, int64_t cols);
+int tfx_finalize_weights(tfx_handle h);
+
+/* ---- per-request set-up --------------------------------------------------------------------------------------- */
+/* Sizes workspaces and TMA descriptors for batch B, S image tokens, T text tokens per sample. */
+int tfx_prepare(tfx_handle h, int32_t B, int32_t S, int32_t T);
+
+/* ---- the hot path ------------------------------------------------------------------------------------------- */
+/* replaces FluxTransformer2DModel.forward (transformer_flux.py:1028-1212) as called at pipeline_flux_fill.py:2084.
+ *   hidden_states [B,S,in_channels]   encoder_hidden_states [B,T,joint_attention_dim]   pooled [B,pooled_dim]
+ *   timestep [B] bf16 (= t/1000, as the pipeline passes it)     guidance [B] fp32 or NULL when !guidance_embeds
+ *   img_ids [S,3] bf16   txt_ids [T,3] bf16      out_sample [B,S,out_channels]
+ */
+int tfx_forward(tfx_handle h, const void* hidden_states, const void* encoder_hidden_states, const void* pooled,
+                const void* timestep_bf16, const void* guidance_f32, const void* img_ids, const void* txt_ids,
+                void* out_sample, void* stream);
+
+/* replaces FlowMatchEulerDiscreteScheduler.step (schedulers/scheduling_flow_match_euler_discrete.py:265-338):
+ *   prev = bf16(fp32(sample) + bf16(bf16(sigma_next - sigma) * model_output)),  n elements. */
+int tfx_euler_step(const void* model_output, const void* sample, void* prev_sample, int64_t n, float sigma,
+                   float sigma_next, void* stream);
+
+/* One whole sampling step = loop body of pipeline_flux_fill.py:2082-2098 in one call: cat(latents, cond) -> forward
+ * -> Euler update fused into the last GEMM's store.  latents_in/out [B,S,out_channels] (may alias),
+ * cond [B,S,in_channels-out_channels], noise_pred_out optional (NULL to skip). */
+int tfx_step(tfx_handle h, const void* latents_in, const void* cond, const void* encoder_hidden_states,
+             const void* pooled, const void* timestep_bf16, const void* guidance_f32, const void* img_ids,
+             const void* txt_ids, float sigma, float sigma_next, void* latents_out, void* noise_pred_out, void* stream);
+
+/* ---- single kernels, exported for parity tests against the oracle --------------------------------------------- */
+/* Y = epilogue(A[M,K] W[N,K]^T + bias); mode: 0 store, 1 gelu-tanh, 2 out = res + gate*(.) (gate [N], res [M,N]) */
+int tfx_op_linear(const void* A, int64_t lda, const void* W, const void* bias, void* out, int64_t ldo, int32_t M,
+                  int32_t N, int32_t K, int32_t mode, const void* gate, const void* res, int32_t cta_group, void* stream);
+/* q,k,v [B,H,N,dh] -> out rows in the engine's [B*T text rows ; B*S image rows] order, row stride ld_out */
+int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int64_t ld_out, int32_t B, int32_t H,
+                     int32_t T, int32_t S, int32_t head_dim, int32_t q_tiles, void* stream);
+/* y = LN(x)*(1+scale)+shift per row; mod [B, mod_stride]; rows = B*rows_per_sample */
+int tfx_op_ln_modulate(const void* x, void* y, int32_t rows, int32_t D, int32_t rows_per_sample, const void* mod,
+                       int64_t mod_stride, int64_t shift_off, int64_t scale_off, void* stream);
+/* y[b,n] = post(sum_k pre(x[b,k]) W[n,k] + bias[n]); flags: 1 silu(x), 2 silu(y), 4 out += y */
+int tfx_op_gemv(const void* x, int32_t B, int32_t K, const void* W, const void* bias, int64_t N, void* out,
+                int32_t flags, void* stream);
+/* (cos,sin) table [T+S, dh/2] float2 from bf16 ids */
+int tfx_op_rope_table(const void* txt_ids, const void* img_ids, int32_t T, int32_t S, const int32_t* axes_dims,
+                      void* out_f32, void* stream);
+/* sinusoidal embedding [B,256] bf16 of bf16(bf16(t)*1000) */
+int tfx_op_timestep_embed(const void* t, int32_t is_f32, int32_t B, void* out, void* stream);
+/* raw tcgen05 descriptor probe (bring-up / regression of the UMMA encodings); see tests/test_gpu_ops.py */
+int tfx_op_umma_probe(const void* A, const void* Bm, void* D_f32, int32_t n_dim, int32_t k_dim, int32_t b_mn_major,
+                      int32_t a_from_tmem, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TEXTFLUX_B200_H_ */

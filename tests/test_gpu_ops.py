@@ -1,0 +1,266 @@
+"""GPU parity of every exported kernel against plain torch fp32 math (through the C ABI, ctypes)."""
+import ctypes as C
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from textflux_b200 import _lib
+    return _lib.load()
+
+
+def _chk(code):
+    from textflux_b200 import _lib
+    _lib.check(code)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-20)).item()
+
+
+# ---------------------------------------------------------------------------------------------- UMMA descriptor probe
+def _probe(lib, A, Bm, n, k, mn, a_tmem, lbo, sbo, kstep):
+    D = torch.full((128, n), float("nan"), device="cuda", dtype=torch.float32)
+    _chk(lib.tfx_op_umma_probe(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), n, k, mn, a_tmem, lbo, sbo, kstep, _stream()))
+    torch.cuda.synchronize()
+    return D
+
+
+@pytest.mark.parametrize("n,k", [(128, 64), (256, 128), (64, 256)])
+@pytest.mark.parametrize("a_tmem", [0, 1])
+def test_umma_kmajor_b(lib, n, k, a_tmem):
+    g = torch.Generator(device="cuda").manual_seed(n * 7 + k)
+    A = torch.randn(128, k, generator=g, device="cuda").to(torch.bfloat16)
+    Bm = torch.randn(n, k, generator=g, device="cuda").to(torch.bfloat16)
+    D = _probe(lib, A, Bm, n, k, 0, a_tmem, 16, 1024, 0)
+    ref = A.float() @ Bm.float().T
+    assert _rel(D, ref) < 1e-5, _rel(D, ref)
+
+
+@pytest.mark.parametrize("n,k", [(128, 128), (64, 128), (128, 64)])
+@pytest.mark.parametrize("a_tmem", [0, 1])
+def test_umma_mnmajor_b(lib, n, k, a_tmem):
+    """B given as [k, n] row-major (the V operand of attention): MN-major descriptor, LBO = distance between the
+    64-wide n blocks (k*128 B), SBO = 1024 B per 8 k-rows, 2048 B per UMMA_K step."""
+    g = torch.Generator(device="cuda").manual_seed(n * 11 + k)
+    A = torch.randn(128, k, generator=g, device="cuda").to(torch.bfloat16)
+    Bm = torch.randn(k, n, generator=g, device="cuda").to(torch.bfloat16)
+    ref = A.float() @ Bm.float()
+    table = {}
+    for lbo, sbo in [(k * 128, 1024), (1024, k * 128), (k * 128, 128), (128, 1024), (16, 1024)]:
+        D = _probe(lib, A, Bm, n, k, 1, a_tmem, lbo, sbo, 2048)
+        table[f"lbo={lbo},sbo={sbo}"] = _rel(D, ref)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", f"probe_mn_n{n}_k{k}_t{a_tmem}.json"), "w") as f:
+        json.dump(table, f, indent=1)
+    print(table)
+    assert table[f"lbo={k * 128},sbo=1024"] < 1e-5, table
+
+
+# ---------------------------------------------------------------------------------------------- GEMM + epilogues
+def _linear(lib, A, W, bias, mode, cta_group, gate=None, res=None, lda=None):
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.zeros(M, N, device="cuda", dtype=torch.bfloat16)
+    if res is not None:
+        out.copy_(res)  # in-place residual, as the engine uses it
+    _chk(lib.tfx_op_linear(A.data_ptr(), lda or A.stride(0), W.data_ptr(), bias.data_ptr(), out.data_ptr(), N, M, N, K, mode,
+                           None if gate is None else gate.data_ptr(), None if res is None else out.data_ptr(), cta_group,
+                           _stream()))
+    torch.cuda.synchronize()
+    return out
+
+
+SHAPES = [(128, 256, 64), (256, 512, 384), (2560, 3072, 3072), (512, 3072, 4096), (80, 256, 128), (64, 64, 256),
+          (200, 768, 1280), (2048, 12288, 3072), (2048, 3072, 15360), (300, 320, 192)]
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_linear_store(lib, M, N, K, cta_group):
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    b = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+    out = _linear(lib, A, W, b, 0, cta_group)
+    ref = A.float() @ W.float().T + b.float()
+    err = _rel(out, ref)
+    assert err < 4e-3, err  # bf16 output rounding ~ 2^-9 relative
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_linear_gelu_and_gate_res(lib, cta_group):
+    M, N, K = 384, 1024, 256
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * 0.06).to(torch.bfloat16)
+    b = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+    lin = (A.float() @ W.float().T + b.float()).to(torch.bfloat16)
+    out = _linear(lib, A, W, b, 1, cta_group)
+    ref = torch.nn.functional.gelu(lin, approximate="tanh")
+    assert _rel(out, ref) < 4e-3
+    gate = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+    res = torch.randn(M, N, generator=g, device="cuda").to(torch.bfloat16)
+    out = _linear(lib, A, W, b, 2, cta_group, gate=gate, res=res)
+    ref = res + gate * lin
+    assert _rel(out, ref) < 4e-3
+
+
+def test_linear_strided_a(lib):
+    """A operand read out of a wider buffer (the [attn | mlp] concat tile): lda > K."""
+    M, N, K, LD = 256, 256, 128, 640
+    g = torch.Generator(device="cuda").manual_seed(9)
+    big = torch.randn(M, LD, generator=g, device="cuda").to(torch.bfloat16)
+    A = big[:, 128:128 + K]
+    W = (torch.randn(N, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    b = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+    out = _linear(lib, A, W, b, 0, 1, lda=LD)
+    assert _rel(out, A.float() @ W.float().T) < 4e-3
+
+
+def test_linear_rejects_bad_k(lib):
+    A = torch.zeros(128, 72, device="cuda", dtype=torch.bfloat16)
+    W = torch.zeros(64, 72, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(ValueError):
+        _linear(lib, A, W, b, 0, 1)
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def _attention(lib, q, k, v, T, q_tiles):
+    B, H, N, dh = q.shape
+    S = N - T
+    out = torch.zeros(B * N, H * dh, device="cuda", dtype=torch.bfloat16)
+    _chk(lib.tfx_op_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), H * dh, B, H, T, S, dh, q_tiles, _stream()))
+    torch.cuda.synchronize()
+    # engine row order: all text rows of all samples, then all image rows
+    txt = out[: B * T].view(B, T, H * dh)
+    img = out[B * T:].view(B, S, H * dh)
+    return torch.cat([txt, img], dim=1)
+
+
+@pytest.mark.parametrize("q_tiles", [1, 2])
+@pytest.mark.parametrize("B,H,T,S,dh", [(1, 2, 128, 128, 128), (1, 24, 512, 2048, 128), (2, 4, 16, 64, 64), (1, 3, 40, 217, 128),
+                                          (2, 2, 100, 412, 64), (1, 1, 0, 128, 128)])
+def test_attention(lib, B, H, T, S, dh, q_tiles):
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + H * 100 + S + dh)
+    N = T + S
+    q = torch.randn(B, H, N, dh, generator=g, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, H, N, dh, generator=g, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B, H, N, dh, generator=g, device="cuda").to(torch.bfloat16)
+    out = _attention(lib, q, k, v, T, q_tiles)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    ref = ref.transpose(1, 2).reshape(B, N, H * dh)
+    err = _rel(out, ref)
+    assert err < 8e-3, err
+
+
+# ---------------------------------------------------------------------------------------------- pointwise kernels
+@pytest.mark.parametrize("rows,D,per", [(80, 256, 40), (2560, 3072, 2560), (96, 1024, 32)])
+def test_ln_modulate(lib, rows, D, per):
+    g = torch.Generator(device="cuda").manual_seed(rows + D)
+    x = (torch.randn(rows, D, generator=g, device="cuda") * 3 + 0.5).to(torch.bfloat16)
+    Bn = rows // per
+    mod = torch.randn(Bn, 3 * D, generator=g, device="cuda").to(torch.bfloat16)
+    y = torch.empty_like(x)
+    _chk(lib.tfx_op_ln_modulate(x.data_ptr(), y.data_ptr(), rows, D, per, mod.data_ptr(), 3 * D, 0, D, _stream()))
+    torch.cuda.synchronize()
+    shift, scale = mod[:, :D], mod[:, D:2 * D]
+    xb = x.view(Bn, per, D)
+    ref = torch.nn.functional.layer_norm(xb, (D,), None, None, 1e-6) * (1 + scale[:, None]) + shift[:, None]
+    ref32 = torch.nn.functional.layer_norm(xb.float(), (D,), None, None, 1e-6) * (1 + scale.float()[:, None]) + shift.float()[:, None]
+    assert _rel(y.view(Bn, per, D), ref32) <= _rel(ref, ref32) * 1.5 + 1e-4
+    assert _rel(y.view(Bn, per, D), ref) < 5e-3
+
+
+@pytest.mark.parametrize("B,K,N,flags", [(1, 256, 3072, 2), (2, 3072, 18432, 1), (3, 32, 256, 2), (8, 3072, 1000, 0), (1, 3072, 4097, 1)])
+def test_gemv(lib, B, K, N, flags):
+    g = torch.Generator(device="cuda").manual_seed(B + K + N)
+    x = torch.randn(B, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * 0.03).to(torch.bfloat16)
+    b = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+    out = torch.zeros(B, N, device="cuda", dtype=torch.bfloat16)
+    _chk(lib.tfx_op_gemv(x.data_ptr(), B, K, W.data_ptr(), b.data_ptr(), N, out.data_ptr(), flags, _stream()))
+    torch.cuda.synchronize()
+    xin = torch.nn.functional.silu(x) if flags & 1 else x
+    ref = torch.nn.functional.linear(xin.float(), W.float(), b.float())
+    if flags & 2:
+        ref = torch.nn.functional.silu(ref.to(torch.bfloat16).float())
+    assert _rel(out, ref) < 5e-3
+    # accumulate flag
+    prev = out.clone()
+    _chk(lib.tfx_op_gemv(x.data_ptr(), B, K, W.data_ptr(), b.data_ptr(), N, out.data_ptr(), flags | 4, _stream()))
+    torch.cuda.synchronize()
+    assert _rel(out, prev.float() * 2) < 5e-3
+
+
+def test_rope_table_matches_float64_reference(lib):
+    T, h2, w2 = 16, 24, 40
+    axes = (16, 56, 56)
+    txt = torch.zeros(T, 3, dtype=torch.bfloat16, device="cuda")
+    ids = torch.zeros(h2, w2, 3)
+    ids[..., 1] += torch.arange(h2)[:, None]
+    ids[..., 2] += torch.arange(w2)[None, :]
+    img = ids.reshape(-1, 3).to(torch.bfloat16).cuda()
+    out = torch.empty(T + h2 * w2, 64, 2, dtype=torch.float32, device="cuda")
+    _chk(lib.tfx_op_rope_table(txt.data_ptr(), img.data_ptr(), T, h2 * w2, (C.c_int32 * 3)(*axes), out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    pos = torch.cat([txt, img]).float().cpu()
+    cs, ss = [], []
+    for a, d in enumerate(axes):
+        fr = 1.0 / (10000.0 ** (torch.arange(0, d, 2, dtype=torch.float64) / d))
+        ang = torch.outer(pos[:, a], fr)
+        cs.append(ang.cos().float())
+        ss.append(ang.sin().float())
+    cos, sin = torch.cat(cs, 1), torch.cat(ss, 1)
+    assert (out[..., 0].cpu() - cos).abs().max().item() < 2e-7
+    assert (out[..., 1].cpu() - sin).abs().max().item() < 2e-7
+    # index exactness: text rows are the identity rotation, axis 0 never rotates
+    assert torch.equal(out[:T, :, 0].cpu(), torch.ones(T, 64)) and torch.equal(out[:T, :, 1].cpu(), torch.zeros(T, 64))
+    assert torch.equal(out[:, :8, 1].cpu(), torch.zeros(T + h2 * w2, 8))
+
+
+def test_timestep_embed(lib):
+    t = (torch.tensor([984.79, 612.5, 33.3, 1000.0]) / 1000).to(torch.bfloat16).cuda()
+    out = torch.empty(4, 256, dtype=torch.bfloat16, device="cuda")
+    _chk(lib.tfx_op_timestep_embed(t.data_ptr(), 0, 4, out.data_ptr(), _stream()))
+    gd = torch.tensor([30.0, 3.5, 1.0, 0.0], device="cuda")
+    outg = torch.empty(4, 256, dtype=torch.bfloat16, device="cuda")
+    _chk(lib.tfx_op_timestep_embed(gd.data_ptr(), 1, 4, outg.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    import math
+
+    def ref(ts):
+        ts = ts.to(torch.bfloat16) * 1000
+        e = torch.exp(-math.log(10000) * torch.arange(128, dtype=torch.float32, device="cuda") / 128)
+        a = ts[:, None].float() * e[None]
+        return torch.cat([torch.cos(a), torch.sin(a)], dim=-1).to(torch.bfloat16)
+
+    assert (out.float() - ref(t).float()).abs().max().item() < 1e-2
+    assert (outg.float() - ref(gd).float()).abs().max().item() < 1e-2
+    assert (out.float() - ref(t).float()).abs().mean().item() < 2e-4
+
+
+def test_euler_step_bit_exact_vs_torch(lib):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    v = torch.randn(2, 300, 64, generator=g, device="cuda").to(torch.bfloat16)
+    x = torch.randn(2, 300, 64, generator=g, device="cuda").to(torch.bfloat16)
+    s0, s1 = torch.tensor(0.731, device="cuda"), torch.tensor(0.702, device="cuda")
+    out = torch.empty_like(x)
+    _chk(lib.tfx_euler_step(v.data_ptr(), x.data_ptr(), out.data_ptr(), v.numel(), 0.731, 0.702, _stream()))
+    torch.cuda.synchronize()
+    ref = (x.to(torch.float32) + (s1 - s0) * v).to(torch.bfloat16)  # exactly the reference's expression on CUDA tensors
+    assert torch.equal(out, ref)

@@ -1,0 +1,13 @@
+"""textflux_b200: Blackwell-native (sm_100a) FLUX-Fill denoising engine behind TextFlux's FluxFillPipeline surface.
+
+Public surface (mirrors what the reference pipeline touches):
+    B200FluxTransformer           drop-in for FluxTransformer2DModel on `pipe.transformer`
+    B200FlowMatchEulerScheduler   drop-in for FlowMatchEulerDiscreteScheduler on `pipe.scheduler`
+    attach(pipe)                  swap both into a loaded FluxFillPipeline
+"""
+from .engine import (B200FlowMatchEulerScheduler, B200FluxTransformer, FrozenConfig, attach,  # noqa: F401
+                     calculate_shift)
+from .packer import fold_lora, pack_weights, reference_names, synthetic_getter  # noqa: F401
+
+__all__ = ["B200FluxTransformer", "B200FlowMatchEulerScheduler", "attach", "calculate_shift", "fold_lora",
+           "pack_weights", "reference_names", "synthetic_getter", "FrozenConfig"]

@@ -1,0 +1,274 @@
+// Joint [text;image] non-causal flash attention on tcgen05 / TMEM / TMA for sm_100a.
+//
+// Replaces F.scaled_dot_product_attention(q, k, v) of FluxAttnProcessor2_0 (attention_processor.py:2039-2043,
+// SURVEY.md §2d K2): q,k,v [B,H,N,dh] bf16 (already RMS-normed and RoPE'd by the QKV GEMM epilogue), scale dh^-0.5,
+// no mask, output written token-major [rows, H*dh] (the transpose+reshape of :2042 is folded into the store, and for
+// single-stream blocks the store lands directly in the [attn | mlp] concat buffer, transformer_flux.py:732).
+//
+// One CTA handles kQTiles x 128 query rows of one (batch, head).  Per 128-row KV tile j and query tile q:
+//     S_q  = Q_q K_j^T      tcgen05.mma SS  (A = Q smem K-major, B = K smem K-major)  -> TMEM fp32 [128 x 128]
+//     P_q  = exp2(S_q*c - m*c)   softmax warpgroup q: one thread per row, running max/sum in registers,
+//                                P written back to TMEM as packed bf16 over the S columns it has consumed
+//     O_q += P_q V_j        tcgen05.mma TS  (A = P from TMEM, B = V smem MN-major)    -> TMEM fp32 [128 x dh]
+// The single MMA-issuing thread interleaves the two query tiles so that softmax of one overlaps the MMAs of the other.
+#pragma once
+#include <cuda.h>
+
+#include "ptx.cuh"
+
+namespace tfx {
+
+struct AttnParams {
+  int B, H, N, T, S;  // N = T + S joint tokens per sample
+  float scale_log2;   // dh^-0.5 * log2(e)
+  __nv_bfloat16* out;
+  long long ld_out;   // row stride of `out` in elements
+};
+
+constexpr int kAttnKvStages = 2;
+
+template <int kHeadDim, int kQTiles>
+struct AttnCfg {
+  static constexpr int kHalves = kHeadDim / 64;             // 64-element (128 B) swizzle atoms along dh
+  static constexpr int kTileBytes = 128 * kHeadDim * 2;     // one 128-row Q/K/V tile
+  static constexpr int kThreads = 64 + 128 * kQTiles;       // TMA warp + MMA warp + softmax warpgroups
+  static constexpr int kSmemBytes = (kQTiles + 2 * kAttnKvStages) * kTileBytes + 1024 + 256;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSCol = 0;                           // S_q at kSCol + q*128 (P aliases its first 64 columns)
+  static constexpr int kOCol = 256;                         // O_q at kOCol + q*128
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int kHeadDim, int kQTiles>
+__global__ void __launch_bounds__(AttnCfg<kHeadDim, kQTiles>::kThreads, 1)
+attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+  using Cfg = AttnCfg<kHeadDim, kQTiles>;
+  constexpr int kHalves = Cfg::kHalves;
+  constexpr int kHalfBytes = 128 * 128;  // 128 rows x 128 B
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                      // [kQTiles][kHalves][128][64]
+  uint8_t* sK = sQ + kQTiles * Cfg::kTileBytes;            // [stages][kHalves][128][64]
+  uint8_t* sV = sK + kAttnKvStages * Cfg::kTileBytes;      // [stages][kHalves][128 kv][64 dh]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kAttnKvStages * Cfg::kTileBytes);
+  uint64_t* q_full = bars;                      // [1]
+  uint64_t* k_full = q_full + 1;                // [stages]
+  uint64_t* v_full = k_full + kAttnKvStages;    // [stages]
+  uint64_t* kv_empty = v_full + kAttnKvStages;  // [stages]
+  uint64_t* s_full = kv_empty + kAttnKvStages;  // [kQTiles]
+  uint64_t* p_full = s_full + kQTiles;          // [kQTiles]
+  uint64_t* pv_done = p_full + kQTiles;         // [kQTiles]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(pv_done + kQTiles);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (128 * kQTiles);
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int bh = b * p.H + head;
+  const int n_kv = (p.N + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQ);
+    prefetch_tensormap(&tmK);
+    prefetch_tensormap(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kAttnKvStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < kQTiles; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(tmem_base_ptr, Cfg::kTmemCols);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_arrive_expect_tx(q_full, kQTiles * Cfg::kTileBytes);
+    for (int q = 0; q < kQTiles; ++q)
+      for (int h = 0; h < kHalves; ++h)
+        tma_load_3d(&tmQ, q_full, sQ + q * Cfg::kTileBytes + h * kHalfBytes, h * 64, q0 + q * 128, bh, kEvictFirst);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      mbar_arrive_expect_tx(&k_full[stage], Cfg::kTileBytes);
+      for (int h = 0; h < kHalves; ++h)
+        tma_load_3d(&tmK, &k_full[stage], sK + stage * Cfg::kTileBytes + h * kHalfBytes, h * 64, j * 128, bh, kEvictLast);
+      mbar_arrive_expect_tx(&v_full[stage], Cfg::kTileBytes);
+      for (int h = 0; h < kHalves; ++h)
+        tma_load_3d(&tmV, &v_full[stage], sV + stage * Cfg::kTileBytes + h * kHalfBytes, h * 64, j * 128, bh, kEvictLast);
+      if (++stage == kAttnKvStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, kHeadDim, 0, 1);  // B = V is MN-major (dh contiguous)
+    auto issue_qk = [&](int q, int stage) {
+      const uint32_t a0 = smem_u32(sQ + q * Cfg::kTileBytes);
+      const uint32_t b0 = smem_u32(sK + stage * Cfg::kTileBytes);
+#pragma unroll
+      for (int kk = 0; kk < kHeadDim / 16; ++kk) {
+        const uint32_t off = uint32_t((kk / 4) * kHalfBytes + (kk % 4) * 32);
+        umma_ss<1>(tmem_base + uint32_t(Cfg::kSCol + q * 128), make_smem_desc(a0 + off, 16, 1024, kLayoutSW128),
+                   make_smem_desc(b0 + off, 16, 1024, kLayoutSW128), idesc_qk, kk != 0);
+      }
+      umma_commit(&s_full[q]);
+    };
+    auto issue_pv = [&](int q, int stage, int j) {
+      const uint32_t v0 = smem_u32(sV + stage * Cfg::kTileBytes);
+#pragma unroll
+      for (int kk = 0; kk < 128 / 16; ++kk) {
+        // 16 kv rows (= 2 KiB) per step; dh halves are kHalfBytes apart (leading-dimension byte offset)
+        umma_ts(tmem_base + uint32_t(Cfg::kOCol + q * 128), tmem_base + uint32_t(Cfg::kSCol + q * 128 + kk * 8),
+                make_smem_desc(v0 + kk * 2048, kHalfBytes, 1024, kLayoutSW128), idesc_pv, (j | kk) != 0);
+      }
+      umma_commit(&pv_done[q]);
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    for (int q = 0; q < kQTiles; ++q) issue_qk(q, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      const int nstage = (stage + 1 == kAttnKvStages) ? 0 : stage + 1;
+      const uint32_t nphase = (stage + 1 == kAttnKvStages) ? phase ^ 1 : phase;
+      mbar_wait(&v_full[stage], phase);
+      for (int q = 0; q < kQTiles; ++q) {
+        mbar_wait(&p_full[q], j & 1);
+        tc_fence_after();
+        issue_pv(q, stage, j);
+        if (q == kQTiles - 1) umma_commit(&kv_empty[stage]);
+        if (j + 1 < n_kv) {
+          if (q == 0) { mbar_wait(&k_full[nstage], nphase); tc_fence_after(); }
+          issue_qk(q, nstage);
+        }
+      }
+      stage = nstage;
+      phase = nphase;
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax warpgroups: one thread per query row =====================
+    const int q = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int row_in_tile = quad * 32 + lane;
+    const int pos = q0 + q * 128 + row_in_tile;
+    const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16);
+    const uint32_t t_s = t_lane + uint32_t(Cfg::kSCol + q * 128);
+    const uint32_t t_o = t_lane + uint32_t(Cfg::kOCol + q * 128);
+    const float c = p.scale_log2;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int valid = min(128, p.N - j * 128);  // columns of this tile that are real keys
+      mbar_wait(&s_full[q], j & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int cch = 0; cch < 4; ++cch) {
+        uint32_t v[32];
+        tmem_ld32(t_s + cch * 32, v);
+        tmem_ld_wait();
+        if (valid >= (cch + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (cch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = ex2((m - m_new) * c);  // 0 on the first tile (m = -inf)
+      const float mc = m_new * c;
+      float rowsum = 0.f;
+#pragma unroll 1
+      for (int cch = 0; cch < 4; ++cch) {
+        uint32_t v[32];
+        uint32_t pk[16];
+        tmem_ld32(t_s + cch * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2(fmaf(__uint_as_float(v[i]), c, -mc));
+          float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), c, -mc));
+          if (cch * 32 + i >= valid) p0 = 0.f;
+          if (cch * 32 + i + 1 >= valid) p1 = 0.f;
+          rowsum += p0 + p1;
+          pk[i / 2] = pack_bf16(p0, p1);
+        }
+        tmem_st16(t_s + cch * 16, pk);  // P (bf16 pairs) over S columns already consumed
+      }
+      l = l * alpha + rowsum;
+      m = m_new;
+      tmem_st_wait();
+      if (j > 0) {
+        mbar_wait(&pv_done[q], (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll 1
+          for (int cch = 0; cch < kHeadDim / 32; ++cch) {
+            uint32_t v[32];
+            tmem_ld32(t_o + cch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(t_o + cch * 32, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[q]);
+    }
+    // ---- finalize: O / l -> bf16, token-major store
+    mbar_wait(&pv_done[q], (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const bool row_ok = pos < p.N;
+    const long long row = (pos < p.T) ? (long long)b * p.T + pos : (long long)p.B * p.T + (long long)b * p.S + (pos - p.T);
+    __nv_bfloat16* dst = p.out + row * p.ld_out + head * kHeadDim;
+#pragma unroll 1
+    for (int cch = 0; cch < kHeadDim / 32; ++cch) {
+      uint32_t v[32];
+      tmem_ld32(t_o + cch * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + cch * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(v[8 * i + 0]) * inv_l, __uint_as_float(v[8 * i + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(v[8 * i + 2]) * inv_l, __uint_as_float(v[8 * i + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(v[8 * i + 4]) * inv_l, __uint_as_float(v[8 * i + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(v[8 * i + 6]) * inv_l, __uint_as_float(v[8 * i + 7]) * inv_l);
+          d4[i] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+}
+
+}  // namespace tfx

@@ -1,0 +1,383 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   Y[m, n] = sum_k A[m, k] * W[n, k]  (+ bias[n])  -> epilogue
+//
+// A (activations, [M,K] row-major bf16) and W (nn.Linear weight, [N,K] row-major bf16) are both K-major, which is
+// exactly the UMMA "TN" case: TMA drops 128B-swizzled [rows x 64] bf16 boxes into shared memory, one elected thread
+// issues tcgen05.mma (kind::f16, fp32 accumulate) into TMEM, four epilogue warps read the accumulator back with
+// tcgen05.ld and apply the fused epilogue.  Replaces every `nn.Linear` call site of the reference hot path
+// (transformer_flux.py:694-696,894-895,920; attention_processor.py:237-260; attention.py:1218-1232)
+// and, through the epilogues, K4-K8 and K10 (RMSNorm, RoPE, GELU, gate+residual, cat, Euler step).
+//
+// kCtaGroup = 1: one CTA owns a 128 x 256 tile.   kCtaGroup = 2: a CTA pair (cluster of 2) owns 256 x 256, the leader
+// CTA issues cta_group::2 MMAs, each CTA loads its 128 rows of A and its 128 rows of W (halved smem traffic per SM).
+//
+// Up to two row groups per launch (text rows / image rows of the double-stream blocks: same N,K, different
+// weights, bias, modulation vectors) so both streams share one persistent grid.
+#pragma once
+#include <cuda.h>
+
+#include "ptx.cuh"
+
+namespace tfx {
+
+enum EpiMode : int {
+  EPI_STORE = 0,     // out = bf16(acc + bias)
+  EPI_GELU = 1,      // out = bf16(gelu_tanh(bf16(acc + bias)))
+  EPI_GATE_RES = 2,  // out = bf16(res + bf16(gate * bf16(acc + bias)))
+  EPI_QKV = 3,       // per-head RMSNorm + RoPE on q,k; scatter q,k,v head-major into the joint [text;image] buffers
+  EPI_EULER = 4,     // v = bf16(acc + bias); latents' = bf16(latents + bf16(dt * v))   (scheduler step fused)
+};
+
+struct GemmGroup {
+  int M;                // rows of this group
+  int rows_per_sample;  // rows of one batch sample inside the group
+  int pos_offset;       // joint-sequence position of a sample's first row (0 for text, T for image)
+  const __nv_bfloat16* bias;  // [N]
+  __nv_bfloat16* out;         // STORE/GELU/GATE_RES/EULER(noise_pred, may be null) destination (first row of group)
+  long long ldo;
+  const __nv_bfloat16* res;   // GATE_RES residual / EULER latents in
+  long long ldr;
+  const __nv_bfloat16* gate;  // GATE_RES: gate vector of sample b at gate + b * gate_stride
+  long long gate_stride;
+  const __nv_bfloat16* rms_q;  // QKV: RMSNorm weights [head_dim]
+  const __nv_bfloat16* rms_k;
+  __nv_bfloat16* out2;  // EULER: latents out
+};
+
+struct GemmParams {
+  int N, K;
+  int num_groups;
+  GemmGroup g[2];
+  int n_split;  // columns [0,n_split) run mode0, [n_split,N) run mode1 (n_split multiple of 256, or == N)
+  int mode0, mode1;
+  int col_offset1;  // mode1 output column = n - n_split + col_offset1
+  // QKV scatter
+  int D, head_dim, num_heads, n_joint;
+  __nv_bfloat16 *q, *k, *v;  // [B, H, n_joint, head_dim]
+  const float2* rope;        // [n_joint, head_dim/2] (cos, sin)
+  float rms_eps;
+  const float* dt_ptr;  // EULER: device scalar float(bf16(sigma_next - sigma))
+};
+
+constexpr int kGemmBlockN = 256;
+constexpr int kGemmBlockK = 64;
+constexpr int kGemmThreads = 256;
+
+template <int kCtaGroup>
+struct GemmCfg {
+  static constexpr int kTileM = 128 * kCtaGroup;
+  static constexpr int kBRows = kGemmBlockN / kCtaGroup;  // rows of W each CTA loads
+  static constexpr int kABytes = 128 * kGemmBlockK * 2;
+  static constexpr int kBBytes = kBRows * kGemmBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kCtaGroup == 1) ? 4 : 6;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&x)[32]) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16(x[8 * i + 0], x[8 * i + 1]);
+    u.y = pack_bf16(x[8 * i + 2], x[8 * i + 3]);
+    u.z = pack_bf16(x[8 * i + 4], x[8 * i + 5]);
+    u.w = pack_bf16(x[8 * i + 6], x[8 * i + 7]);
+    d4[i] = u;
+  }
+}
+// kReadOnly: data never written during the kernel (bias, gates, norm weights) -> ld.global.nc
+template <bool kReadOnly = true>
+__device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&x)[32]) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u = kReadOnly ? __ldg(s4 + i) : s4[i];
+    x[8 * i + 0] = bf16_lo(u.x); x[8 * i + 1] = bf16_hi(u.x);
+    x[8 * i + 2] = bf16_lo(u.y); x[8 * i + 3] = bf16_hi(u.y);
+    x[8 * i + 4] = bf16_lo(u.z); x[8 * i + 5] = bf16_hi(u.z);
+    x[8 * i + 6] = bf16_lo(u.w); x[8 * i + 7] = bf16_hi(u.w);
+  }
+}
+
+// acc chunk (32 fp32 columns of this thread's row) + bias -> bf16-rounded linear output, as nn.Linear returns it
+__device__ __forceinline__ void linear_out(const uint32_t (&v)[32], const __nv_bfloat16* bias, int n, int N, float (&x)[32]) {
+  float b[32];
+  if (n + 32 <= N) {
+    load_bf16x32(bias + n, b);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) b[i] = (n + i < N) ? __bfloat162float(bias[n + i]) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) x[i] = bf16_round(__uint_as_float(v[i]) + b[i]);
+}
+
+template <int kCtaGroup>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                    const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                    const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<kCtaGroup>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0;
+  const bool is_leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA0);
+    prefetch_tensormap(&tmB0);
+    if (p.num_groups > 1) {
+      prefetch_tensormap(&tmA1);
+      prefetch_tensormap(&tmB1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4 * kCtaGroup);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<kCtaGroup>(tmem_base_ptr, 512);
+    tmem_relinquish<kCtaGroup>();
+  }
+  tc_fence_before();
+  if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  // ---- tile schedule (identical in every role)
+  const int mt0 = (p.g[0].M + Cfg::kTileM - 1) / Cfg::kTileM;
+  const int mt1 = (p.num_groups > 1) ? (p.g[1].M + Cfg::kTileM - 1) / Cfg::kTileM : 0;
+  const int MT = mt0 + mt1;
+  const int NT = (p.N + kGemmBlockN - 1) / kGemmBlockN;
+  const int num_tiles = MT * NT;
+  const int KB = p.K / kGemmBlockK;
+  const int first_tile = blockIdx.x / kCtaGroup;
+  const int tile_step = gridDim.x / kCtaGroup;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      const int mi = t % MT, ni = t / MT;
+      const int grp = (mi < mt0) ? 0 : 1;
+      const int m0 = (grp ? mi - mt0 : mi) * Cfg::kTileM + int(cta_rank) * 128;
+      const int n0 = ni * kGemmBlockN + int(cta_rank) * Cfg::kBRows;
+      const CUtensorMap* tA = grp ? &tmA1 : &tmA0;
+      const CUtensorMap* tB = grp ? &tmB1 : &tmB0;
+      for (int kb = 0; kb < KB; ++kb) {
+        if constexpr (kCtaGroup == 2) mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+        else mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCtaGroup);
+        uint8_t* sa = smem_a + stage * Cfg::kABytes;
+        uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+        if constexpr (kCtaGroup == 2) {
+          tma_load_2d_2sm(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, kEvictNormal);
+          tma_load_2d_2sm(tB, &full_bar[stage], sb, kb * kGemmBlockK, n0, kEvictNormal);
+        } else {
+          tma_load_2d(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, kEvictNormal);
+          tma_load_2d(tB, &full_bar[stage], sb, kb * kGemmBlockK, n0, kEvictNormal);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (is_leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(Cfg::kTileM, kGemmBlockN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
+        if constexpr (kCtaGroup == 2) mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
+        else mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * kGemmBlockN);
+        for (int kb = 0; kb < KB; ++kb) {
+          if constexpr (kCtaGroup == 2) mbar_wait_cluster(&full_bar[stage], phase);
+          else mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_a + stage * Cfg::kABytes);
+          const uint32_t sb = smem_u32(smem_b + stage * Cfg::kBBytes);
+          const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
+          const uint64_t db = make_smem_desc(sb, 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kGemmBlockK / 16; ++k) {
+            // +32 bytes (= 2 in 16-byte units) per UMMA_K step inside the 128B swizzle atom
+            umma_ss<kCtaGroup>(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+          }
+          if constexpr (kCtaGroup == 2) umma_commit_2sm(&empty_bar[stage], 0b11);
+          else umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (kCtaGroup == 2) umma_commit_2sm(&tmem_full_bar[acc], 0b11);
+        else umma_commit(&tmem_full_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = first_tile; t < num_tiles; t += tile_step) {
+      const int mi = t % MT, ni = t / MT;
+      const int grp = (mi < mt0) ? 0 : 1;
+      const GemmGroup& G = p.g[grp];
+      const int m_local = (grp ? mi - mt0 : mi) * Cfg::kTileM + int(cta_rank) * 128 + quad * 32 + lane;
+      const bool row_ok = m_local < G.M;
+      const int n_tile0 = ni * kGemmBlockN;
+      const int mode = (n_tile0 < p.n_split) ? p.mode0 : p.mode1;
+      const int bidx = m_local / G.rows_per_sample;
+      const int pos = G.pos_offset + (m_local - bidx * G.rows_per_sample);
+
+      if constexpr (kCtaGroup == 2) mbar_wait_cluster(&tmem_full_bar[acc], acc_phase);
+      else mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * kGemmBlockN);
+
+      if (mode == EPI_QKV) {
+        const int sect = n_tile0 / p.D;  // 0 q, 1 k, 2 v
+        const int dh = p.head_dim;
+        const int head0 = (n_tile0 - sect * p.D) / dh;
+        const int heads_in_tile = kGemmBlockN / dh;
+        const int chunks_per_head = dh / 32;
+        __nv_bfloat16* dst_base = (sect == 0) ? p.q : (sect == 1) ? p.k : p.v;
+        const __nv_bfloat16* rmsw = (sect == 0) ? G.rms_q : G.rms_k;
+        for (int hh = 0; hh < heads_in_tile; ++hh) {
+          const int head = head0 + hh;
+          if (n_tile0 + hh * dh >= p.N) break;
+          __nv_bfloat16* dst = dst_base + ((long long)(bidx * p.num_heads + head) * p.n_joint + pos) * dh;
+          float rstd = 0.f;
+          if (sect < 2) {
+            float ss = 0.f;
+            for (int c = 0; c < chunks_per_head; ++c) {
+              uint32_t v[32];
+              float x[32];
+              tmem_ld32(t_acc + uint32_t(hh * dh + c * 32), v);
+              tmem_ld_wait();
+              linear_out(v, G.bias, n_tile0 + hh * dh + c * 32, p.N, x);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) ss = fmaf(x[i], x[i], ss);
+            }
+            rstd = rsqrtf(ss / float(dh) + p.rms_eps);
+          }
+          for (int c = 0; c < chunks_per_head; ++c) {
+            uint32_t v[32];
+            float x[32];
+            tmem_ld32(t_acc + uint32_t(hh * dh + c * 32), v);
+            tmem_ld_wait();
+            linear_out(v, G.bias, n_tile0 + hh * dh + c * 32, p.N, x);
+            if (sect < 2) {
+              float w[32];
+              load_bf16x32(rmsw + c * 32, w);
+              // RMSNorm.forward: (x * rsqrt(var+eps)) -> bf16 -> * weight(bf16) -> bf16   (normalization.py:535-546)
+#pragma unroll
+              for (int i = 0; i < 32; ++i) x[i] = bf16_round(bf16_round(x[i] * rstd) * w[i]);
+              // apply_rotary_emb: fp32 x*cos + rot(x)*sin on interleaved pairs (embeddings.py:904-914)
+              if (row_ok) {
+                const float4* cs4 = reinterpret_cast<const float4*>(p.rope + (long long)pos * (dh / 2) + c * 16);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float4 cs = __ldg(cs4 + i);  // (cos0, sin0, cos1, sin1)
+                  float a0 = x[4 * i + 0], a1 = x[4 * i + 1], b0 = x[4 * i + 2], b1 = x[4 * i + 3];
+                  x[4 * i + 0] = __fadd_rn(__fmul_rn(a0, cs.x), __fmul_rn(-a1, cs.y));
+                  x[4 * i + 1] = __fadd_rn(__fmul_rn(a1, cs.x), __fmul_rn(a0, cs.y));
+                  x[4 * i + 2] = __fadd_rn(__fmul_rn(b0, cs.z), __fmul_rn(-b1, cs.w));
+                  x[4 * i + 3] = __fadd_rn(__fmul_rn(b1, cs.z), __fmul_rn(b0, cs.w));
+                }
+              }
+            }
+            if (row_ok) store_bf16x32(dst + c * 32, x);
+          }
+        }
+      } else {
+        const int n_out0 = (n_tile0 < p.n_split) ? n_tile0 : (n_tile0 - p.n_split + p.col_offset1);
+        for (int c = 0; c < kGemmBlockN / 32; ++c) {
+          const int n = n_tile0 + c * 32;
+          if (n >= p.N) break;  // warp-uniform
+          uint32_t v[32];
+          float x[32];
+          tmem_ld32(t_acc + uint32_t(c * 32), v);
+          tmem_ld_wait();
+          linear_out(v, G.bias, n, p.N, x);
+          const int no = n_out0 + c * 32;
+          if (mode == EPI_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] = gelu_tanh(x[i]);
+          } else if (mode == EPI_GATE_RES) {
+            if (row_ok) {
+              float g[32], r[32];
+              load_bf16x32(G.gate + (long long)bidx * G.gate_stride + n, g);
+              load_bf16x32<false>(G.res + (long long)m_local * G.ldr + no, r);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) x[i] = r[i] + bf16_round(g[i] * x[i]);
+            }
+          } else if (mode == EPI_EULER) {
+            if (row_ok) {
+              const float dt = __ldg(p.dt_ptr);
+              if (n + 32 <= p.N) {
+                float r[32], y[32];
+                if (G.out) store_bf16x32(G.out + (long long)m_local * G.ldo + no, x);
+                load_bf16x32<false>(G.res + (long long)m_local * G.ldr + no, r);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) y[i] = r[i] + bf16_round(dt * x[i]);
+                store_bf16x32(G.out2 + (long long)m_local * G.ldr + no, y);
+              } else {
+                for (int i = 0; i < 32 && n + i < p.N; ++i) {
+                  if (G.out) G.out[(long long)m_local * G.ldo + no + i] = __float2bfloat16_rn(x[i]);
+                  float r = __bfloat162float(G.res[(long long)m_local * G.ldr + no + i]);
+                  G.out2[(long long)m_local * G.ldr + no + i] = __float2bfloat16_rn(r + bf16_round(dt * x[i]));
+                }
+              }
+            }
+            continue;
+          }
+          if (row_ok) {
+            if (n + 32 <= p.N) {
+              store_bf16x32(G.out + (long long)m_local * G.ldo + no, x);
+            } else {
+              for (int i = 0; i < 32 && n + i < p.N; ++i) G.out[(long long)m_local * G.ldo + no + i] = __float2bfloat16_rn(x[i]);
+            }
+          }
+        }
+      }
+      // release this accumulator stage back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCtaGroup == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<kCtaGroup>(tmem_base, 512);
+}
+
+}  // namespace tfx

@@ -1,0 +1,213 @@
+// HBM/latency-bound kernels of the hot path: sinusoidal embeddings, small-batch GEMV (temb MLPs and the 344*D-row
+// adaLN modulation matrix), LayerNorm+modulate, RoPE table, Euler update.  All follow the reference's bf16 rounding
+// points (each eager op of the reference returns bf16) so results track the reference to the last bit where the
+// arithmetic order allows.
+#pragma once
+#include "ptx.cuh"
+
+namespace tfx {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0) applied to  bf16(bf16(t) * 1000)
+// (transformer_flux.py:1088-1090 then embeddings.py:27-78,1330-1334).  out [B,256] bf16 = [cos | sin].
+// in_is_f32: guidance arrives fp32, timestep arrives bf16.
+__global__ void timestep_embed_kernel(const void* __restrict__ t_in, int in_is_f32, int B, __nv_bfloat16* __restrict__ out) {
+  const int b = blockIdx.x;
+  const int k = threadIdx.x;  // 0..127
+  if (b >= B || k >= 128) return;
+  float t = in_is_f32 ? reinterpret_cast<const float*>(t_in)[b] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(t_in)[b]);
+  t = bf16_round(bf16_round(t) * 1000.0f);
+  const float exponent = (-9.210340371976184f * float(k)) / 128.0f;  // -ln(10000) * k / half_dim, fp32 like torch
+  const float arg = t * expf(exponent);
+  out[b * 256 + k] = __float2bfloat16_rn(cosf(arg));
+  out[b * 256 + 128 + k] = __float2bfloat16_rn(sinf(arg));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small-batch GEMV:  y[b, n] = post( sum_k pre(x[b, k]) * W[n, k] + bias[n] )  ;  optional  out = bf16(out + y)
+// One warp per output row n, all (<= 8) batch rows at once; W streamed once with 16-byte loads.
+// Used for TimestepEmbedding / PixArtAlphaTextProjection (embeddings.py:1009-1021,1927-1932) and for all 77 adaLN
+// `linear(silu(temb))` calls at once (normalization.py:167,200,363) via the concatenated [344*D, D] matrix.
+enum GemvFlags : int { GEMV_PRE_SILU = 1, GEMV_POST_SILU = 2, GEMV_ADD_TO_OUT = 4 };
+constexpr int kGemvMaxB = 8;
+
+__global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restrict__ x, int B, int K,
+                                                  const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ bias,
+                                                  long long N, __nv_bfloat16* out, int flags) {
+  extern __shared__ __nv_bfloat16 xs[];  // [B][K], pre-activation applied (bf16 like the reference's silu output)
+  for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
+    float v = __bfloat162float(x[i]);
+    if (flags & GEMV_PRE_SILU) v = bf16_round(silu(v));
+    xs[i] = __float2bfloat16_rn(v);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long num_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const int kvec = K >> 3;  // uint4 per row
+  for (long long n = warp_global; n < N; n += num_warps) {
+    const uint4* wrow = reinterpret_cast<const uint4*>(W + n * K);
+    float acc[kGemvMaxB];
+#pragma unroll
+    for (int b = 0; b < kGemvMaxB; ++b) acc[b] = 0.f;
+    for (int v0 = lane; v0 < kvec; v0 += 128) {
+      uint4 w4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int vi = v0 + u * 32;
+        w4[u] = (vi < kvec) ? __ldg(wrow + vi) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int vi = v0 + u * 32;
+        if (vi >= kvec) continue;
+        const uint32_t wu[4] = {w4[u].x, w4[u].y, w4[u].z, w4[u].w};
+#pragma unroll
+        for (int b = 0; b < kGemvMaxB; ++b) {
+          if (b >= B) break;
+          const uint4 xv = *reinterpret_cast<const uint4*>(xs + b * K + vi * 8);
+          const uint32_t xu[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            acc[b] = fmaf(bf16_lo(wu[e]), bf16_lo(xu[e]), acc[b]);
+            acc[b] = fmaf(bf16_hi(wu[e]), bf16_hi(xu[e]), acc[b]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < kGemvMaxB; ++b) {
+      if (b >= B) break;
+      float s = warp_sum(acc[b]);
+      if (lane == 0) {
+        float y = bf16_round(s + __bfloat162float(bias[n]));
+        if (flags & GEMV_POST_SILU) y = bf16_round(silu(y));
+        if (flags & GEMV_ADD_TO_OUT) y = __bfloat162float(out[(long long)b * N + n]) + y;
+        out[(long long)b * N + n] = __float2bfloat16_rn(y);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// y = LayerNorm(x, eps=1e-6, no affine) * (1 + scale) + shift      (normalization.py:169,201,365;
+// transformer_flux.py:820-821,833-834).  One warp per row, the row lives in registers (kVec uint4 per lane).
+// Rows [0, rows0) belong to samples of rows_per0 rows and read (shift,scale) at mod + b*mod_stride + {shift0,scale0};
+// rows [rows0, rows) likewise with rows_per1 / {shift1,scale1}  (text stream / image stream).
+struct LnModParams {
+  const __nv_bfloat16* x;
+  __nv_bfloat16* y;
+  int rows, D;
+  int row_begin;  // first row to process (norm_out touches image rows only)
+  int rows0, rows_per0, rows_per1;
+  const __nv_bfloat16* mod;
+  long long mod_stride;
+  long long shift0, scale0, shift1, scale1;
+  float eps;
+};
+
+template <int kVec>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnModParams p) {
+  const int lane = threadIdx.x & 31;
+  const int row = p.row_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(p.x + (long long)row * p.D);
+  float v[kVec * 8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const uint4 u = xr[lane + i * 32];
+    v[8 * i + 0] = bf16_lo(u.x); v[8 * i + 1] = bf16_hi(u.x);
+    v[8 * i + 2] = bf16_lo(u.y); v[8 * i + 3] = bf16_hi(u.y);
+    v[8 * i + 4] = bf16_lo(u.z); v[8 * i + 5] = bf16_hi(u.z);
+    v[8 * i + 6] = bf16_lo(u.w); v[8 * i + 7] = bf16_hi(u.w);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sum += v[8 * i + e];
+  }
+  const float mean = warp_sum(sum) / float(p.D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVec * 8; ++i) {
+    const float d = v[i] - mean;
+    sq = fmaf(d, d, sq);
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / float(p.D) + p.eps);
+  int b;
+  long long shift_off, scale_off;
+  if (row < p.rows0) {
+    b = row / p.rows_per0; shift_off = p.shift0; scale_off = p.scale0;
+  } else {
+    b = (row - p.rows0) / p.rows_per1; shift_off = p.shift1; scale_off = p.scale1;
+  }
+  const uint4* sh = reinterpret_cast<const uint4*>(p.mod + (long long)b * p.mod_stride + shift_off);
+  const uint4* sc = reinterpret_cast<const uint4*>(p.mod + (long long)b * p.mod_stride + scale_off);
+  uint4* yr = reinterpret_cast<uint4*>(p.y + (long long)row * p.D);
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) {
+    const uint4 s4 = __ldg(sh + lane + i * 32);
+    const uint4 c4 = __ldg(sc + lane + i * 32);
+    const uint32_t su[4] = {s4.x, s4.y, s4.z, s4.w};
+    const uint32_t cu[4] = {c4.x, c4.y, c4.z, c4.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // eager reference: LN -> bf16 ; (1 + scale) -> bf16 ; product -> bf16 ; + shift -> bf16
+      const float n0 = bf16_round((v[8 * i + 2 * e] - mean) * rstd);
+      const float n1 = bf16_round((v[8 * i + 2 * e + 1] - mean) * rstd);
+      const float a0 = bf16_round(1.0f + bf16_lo(cu[e]));
+      const float a1 = bf16_round(1.0f + bf16_hi(cu[e]));
+      const float y0 = bf16_round(n0 * a0) + bf16_lo(su[e]);
+      const float y1 = bf16_round(n1 * a1) + bf16_hi(su[e]);
+      o[e] = pack_bf16(y0, y1);
+    }
+    yr[lane + i * 32] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FluxPosEmbed (embeddings.py:952-973): float64 frequencies and angles, cast to fp32.  Output [n_joint, dh/2] of
+// (cos, sin) - the reference's repeat_interleave(2) duplicates are not stored.  ids arrive bf16 [*,3].
+struct RopeParams {
+  const __nv_bfloat16* txt_ids;
+  const __nv_bfloat16* img_ids;
+  int T, S;
+  int axes[3];
+  int half_dim;  // dh/2
+  float2* out;
+};
+__global__ void rope_table_kernel(const RopeParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = (p.T + p.S) * p.half_dim;
+  if (idx >= total) return;
+  const int tok = idx / p.half_dim;
+  int j = idx - tok * p.half_dim;
+  int axis = 0;
+  while (axis < 2 && j >= p.axes[axis] / 2) { j -= p.axes[axis] / 2; ++axis; }
+  const __nv_bfloat16* ids = (tok < p.T) ? p.txt_ids + tok * 3 : p.img_ids + (tok - p.T) * 3;
+  const double pos = double(__bfloat162float(ids[axis]));
+  const double dim = double(p.axes[axis]);
+  const double freq = 1.0 / pow(10000.0, double(2 * j) / dim);
+  const double ang = pos * freq;
+  p.out[idx] = make_float2(float(cos(ang)), float(sin(ang)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FlowMatchEulerDiscreteScheduler.step (scheduling_flow_match_euler_discrete.py:322-330):
+//   prev = bf16( float(sample) + float( bf16( float(bf16(dt)) * float(v) ) ) )
+__global__ void euler_step_kernel(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ x,
+                                  __nv_bfloat16* __restrict__ out, long long n, float dt_bf16) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float dv = bf16_round(dt_bf16 * __bfloat162float(v[i]));
+  out[i] = __float2bfloat16_rn(__bfloat162float(x[i]) + dv);
+}
+
+__global__ void set_float_kernel(float* dst, float value) { *dst = value; }
+
+}  // namespace tfx

@@ -1,0 +1,946 @@
+// C-ABI implementation (include/textflux_b200.h): model state, workspace, TMA descriptors, the per-step launch
+// sequence of FluxTransformer2DModel.forward (transformer_flux.py:1028-1212) and CUDA-graph replay of it.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/textflux_b200.h"
+#include "attention.cuh"
+#include "gemm.cuh"
+#include "pointwise.cuh"
+#include "probe.cuh"
+
+using namespace tfx;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct Fail {
+  int code;
+};
+
+int set_error(std::string* dst, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  if (dst) *dst = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                    \
+  do {                                                                                                    \
+    cudaError_t _e = (expr);                                                                              \
+    if (_e != cudaSuccess) {                                                                              \
+      set_error(err_, TFX_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      throw Fail{TFX_ERR_CUDA};                                                                           \
+    }                                                                                                     \
+  } while (0)
+
+#define REQUIRE(cond, code, ...)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      set_error(err_, code, __VA_ARGS__);        \
+      throw Fail{code};                          \
+    }                                            \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn(std::string* err_) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+  REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, TFX_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with row stride ld (elements); box = [box_rows x 64 cols], 128B swizzle.
+CUtensorMap make_map_2d(std::string* err_, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  CUtensorMap m;
+  memset(&m, 0, sizeof m);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0, TFX_ERR_INVALID,
+          "TMA operand must be 16-byte aligned (ptr %p, ld %lld)", ptr, ld);
+  CUresult r = get_encode_fn(err_)(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REQUIRE(r == CUDA_SUCCESS, TFX_ERR_CUDA, "cuTensorMapEncodeTiled(2d %lldx%lld ld %lld box %d) failed: %d", rows, cols, ld,
+          box_rows, (int)r);
+  return m;
+}
+
+// 3-D bf16 [outer, rows, cols] contiguous; box = [1, 128 rows, 64 cols]
+CUtensorMap make_map_3d(std::string* err_, const void* ptr, long long outer, long long rows, long long cols) {
+  CUtensorMap m;
+  memset(&m, 0, sizeof m);
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)outer};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode_fn(err_)(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REQUIRE(r == CUDA_SUCCESS, TFX_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
+  return m;
+}
+
+int num_sms(int device) {
+  static std::map<int, int> cache;
+  auto it = cache.find(device);
+  if (it != cache.end()) return it->second;
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+  cache[device] = n;
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+struct LaunchCtx {
+  cudaStream_t stream;
+  int device;
+  long long* counter;
+  std::string* err_;
+};
+
+void configure_kernels(std::string* err_) {
+  static bool done = false;
+  if (done) return;
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 1>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 1>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  done = true;
+}
+
+void launch_gemm(const LaunchCtx& c, int cta_group, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
+                 const CUtensorMap& b1, const GemmParams& p) {
+  std::string* err_ = c.err_;
+  REQUIRE(p.K % kGemmBlockK == 0 && p.K > 0, TFX_ERR_INVALID, "GEMM K=%d must be a positive multiple of %d", p.K, kGemmBlockK);
+  REQUIRE(p.n_split == p.N || p.n_split % kGemmBlockN == 0, TFX_ERR_INVALID, "n_split %d not tile aligned", p.n_split);
+  const int tile_m = 128 * cta_group;
+  long long tiles = 0;
+  for (int g = 0; g < p.num_groups; ++g) tiles += (p.g[g].M + tile_m - 1) / tile_m;
+  tiles *= (p.N + kGemmBlockN - 1) / kGemmBlockN;
+  if (tiles == 0) return;
+  const int sms = num_sms(c.device);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.stream = c.stream;
+  if (cta_group == 2) {
+    long long clusters = tiles < sms / 2 ? tiles : sms / 2;
+    cfg.gridDim = dim3((unsigned)(clusters * 2));
+    cfg.dynamicSmemBytes = GemmCfg<2>::kSmemBytes;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, a0, a1, b0, b1, p));
+  } else {
+    cfg.gridDim = dim3((unsigned)(tiles < sms ? tiles : sms));
+    cfg.dynamicSmemBytes = GemmCfg<1>::kSmemBytes;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1>, a0, a1, b0, b1, p));
+  }
+  ++*c.counter;
+}
+
+void launch_attention(const LaunchCtx& c, int head_dim, int q_tiles, const CUtensorMap& tq, const CUtensorMap& tk,
+                      const CUtensorMap& tv, const AttnParams& p) {
+  std::string* err_ = c.err_;
+  REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
+  REQUIRE(q_tiles == 1 || q_tiles == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
+  dim3 grid((p.N + 128 * q_tiles - 1) / (128 * q_tiles), p.H, p.B);
+  if (head_dim == 128 && q_tiles == 2)
+    attention_tcgen05_kernel<128, 2><<<grid, AttnCfg<128, 2>::kThreads, AttnCfg<128, 2>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
+  else if (head_dim == 128)
+    attention_tcgen05_kernel<128, 1><<<grid, AttnCfg<128, 1>::kThreads, AttnCfg<128, 1>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
+  else if (q_tiles == 2)
+    attention_tcgen05_kernel<64, 2><<<grid, AttnCfg<64, 2>::kThreads, AttnCfg<64, 2>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
+  else
+    attention_tcgen05_kernel<64, 1><<<grid, AttnCfg<64, 1>::kThreads, AttnCfg<64, 1>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
+  CUDA_TRY(cudaGetLastError());
+  ++*c.counter;
+}
+
+void launch_ln_modulate(const LaunchCtx& c, const LnModParams& p) {
+  std::string* err_ = c.err_;
+  REQUIRE(p.D % 256 == 0, TFX_ERR_INVALID, "LayerNorm width %d must be a multiple of 256", p.D);
+  const int rows = p.rows - p.row_begin;
+  if (rows <= 0) return;
+  const int blocks = (rows + 7) / 8;
+  switch (p.D / 256) {
+    case 1: ln_modulate_kernel<1><<<blocks, 256, 0, c.stream>>>(p); break;
+    case 2: ln_modulate_kernel<2><<<blocks, 256, 0, c.stream>>>(p); break;
+    case 4: ln_modulate_kernel<4><<<blocks, 256, 0, c.stream>>>(p); break;
+    case 8: ln_modulate_kernel<8><<<blocks, 256, 0, c.stream>>>(p); break;
+    case 12: ln_modulate_kernel<12><<<blocks, 256, 0, c.stream>>>(p); break;
+    case 16: ln_modulate_kernel<16><<<blocks, 256, 0, c.stream>>>(p); break;
+    default: REQUIRE(false, TFX_ERR_INVALID, "LayerNorm width %d unsupported", p.D);
+  }
+  CUDA_TRY(cudaGetLastError());
+  ++*c.counter;
+}
+
+void launch_gemv(const LaunchCtx& c, const bf16* x, int B, int K, const bf16* W, const bf16* bias, long long N, bf16* out, int flags) {
+  std::string* err_ = c.err_;
+  REQUIRE(K % 8 == 0, TFX_ERR_INVALID, "GEMV K=%d must be a multiple of 8", K);
+  REQUIRE(B >= 1 && B <= kGemvMaxB, TFX_ERR_INVALID, "batch %d unsupported (1..%d)", B, kGemvMaxB);
+  const size_t smem = (size_t)B * K * 2;
+  REQUIRE(smem <= 48 * 1024, TFX_ERR_INVALID, "GEMV input %zu bytes exceeds 48 KiB", smem);
+  long long blocks = (N + 7) / 8;
+  const long long cap = (long long)num_sms(c.device) * 8;
+  if (blocks > cap) blocks = cap;
+  gemv_kernel<<<(unsigned)blocks, 256, smem, c.stream>>>(x, B, K, W, bias, N, out, flags);
+  CUDA_TRY(cudaGetLastError());
+  ++*c.counter;
+}
+
+struct Weight {
+  const bf16* ptr = nullptr;
+  long long rows = 0, cols = 0;
+};
+
+}  // namespace
+
+// ==================================================================================================== model
+struct tfx_model {
+  tfx_config cfg;
+  int device = 0;
+  std::string err;
+  std::string* err_ = &err;
+  long long launches = 0;
+  long long graph_nodes = 0;
+  int gemm_cta_group = 1;
+  int attn_q_tiles = 2;
+  int use_graph = 1;
+  bool finalized = false;
+  std::map<std::string, Weight> w;
+
+  int D = 0, H = 0, dh = 0;
+  long long mod_rows = 0;
+
+  // per-request state
+  int B = 0, S = 0, T = 0, N = 0;
+  std::vector<void*> allocs;
+  bf16 *hidden = nullptr, *nbuf = nullptr, *cat = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *mod = nullptr;
+  bf16 *x_in = nullptr, *enc_in = nullptr, *pooled_in = nullptr, *t_in = nullptr, *ids_txt = nullptr, *ids_img = nullptr;
+  bf16 *tproj = nullptr, *h1 = nullptr, *temb = nullptr, *out_buf = nullptr, *lat_in = nullptr, *lat_out = nullptr;
+  float* g_in = nullptr;
+  float* dt_dev = nullptr;
+  float2* rope = nullptr;
+  // activation-side TMA descriptors, [0] text rows, [1] image rows
+  CUtensorMap mA_nbuf[2], mA_attn[2], mA_mlp[2], mA_cat[2], mA_x, mA_enc, mA_final;
+  CUtensorMap mQ, mK, mV;
+  std::map<std::string, CUtensorMap> mB[3];  // [cta_group] weight-side descriptors by weight name
+
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  cudaGraphExec_t graph_fwd = nullptr, graph_step = nullptr;
+
+  const Weight& W(const std::string& name) {
+    auto it = w.find(name);
+    REQUIRE(it != w.end(), TFX_ERR_MISSING, "weight '%s' was never set", name.c_str());
+    return it->second;
+  }
+  const CUtensorMap& WB(const std::string& name) {
+    auto it = mB[gemm_cta_group].find(name);
+    REQUIRE(it != mB[gemm_cta_group].end(), TFX_ERR_STATE, "no TMA descriptor for '%s'", name.c_str());
+    return it->second;
+  }
+  void free_workspace() {
+    for (void* p : allocs) cudaFree(p);
+    allocs.clear();
+    if (graph_fwd) { cudaGraphExecDestroy(graph_fwd); graph_fwd = nullptr; }
+    if (graph_step) { cudaGraphExecDestroy(graph_step); graph_step = nullptr; }
+    B = S = T = N = 0;
+  }
+  template <typename Tp>
+  Tp* alloc(size_t count) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, count * sizeof(Tp) + 256));
+    allocs.push_back(p);
+    return reinterpret_cast<Tp*>(p);
+  }
+  // modulation-vector offsets inside one sample's [mod_rows] vector
+  long long mod_double(int i, int stream_c, int chunk) const { return ((long long)i * 12 + (stream_c ? 6 : 0) + chunk) * D; }
+  long long mod_single(int j, int chunk) const { return ((long long)cfg.num_layers * 12 + (long long)j * 3 + chunk) * D; }
+  long long mod_final(int chunk) const { return ((long long)cfg.num_layers * 12 + (long long)cfg.num_single_layers * 3 + chunk) * D; }
+
+  void build_weight_maps();
+  void prepare(int B_, int S_, int T_);
+  void enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_noise_pred);
+  void run(bool fused_euler, bool want_noise_pred);
+};
+
+void tfx_model::build_weight_maps() {
+  for (int cg = 1; cg <= 2; ++cg) {
+    mB[cg].clear();
+    for (auto& kv : w) {
+      const std::string& name = kv.first;
+      if (name.size() < 2 || name.compare(name.size() - 2, 2, ".w") != 0) continue;
+      if (name.compare(0, 4, "mod.") == 0 || name.find("_embed.") != std::string::npos) continue;  // GEMV weights
+      const Weight& t = kv.second;
+      REQUIRE(t.cols % kGemmBlockK == 0, TFX_ERR_INVALID, "weight '%s' has K=%lld, not a multiple of %d", name.c_str(), t.cols, kGemmBlockK);
+      mB[cg][name] = make_map_2d(err_, t.ptr, t.rows, t.cols, t.cols, kGemmBlockN / cg);
+    }
+  }
+}
+
+void tfx_model::prepare(int B_, int S_, int T_) {
+  REQUIRE(finalized, TFX_ERR_STATE, "tfx_prepare before tfx_finalize_weights");
+  REQUIRE(B_ >= 1 && B_ <= kGemvMaxB && S_ >= 1 && T_ >= 1, TFX_ERR_INVALID, "unsupported problem B=%d S=%d T=%d", B_, S_, T_);
+  if (B_ == B && S_ == S && T_ == T) return;
+  free_workspace();
+  B = B_; S = S_; T = T_; N = S + T;
+  const long long R = (long long)B * N;
+  hidden = alloc<bf16>(R * D);
+  nbuf = alloc<bf16>(R * D);
+  cat = alloc<bf16>(R * 5 * D);
+  q = alloc<bf16>(R * D);
+  k = alloc<bf16>(R * D);
+  v = alloc<bf16>(R * D);
+  mod = alloc<bf16>((long long)B * mod_rows);
+  x_in = alloc<bf16>((long long)B * S * cfg.in_channels);
+  enc_in = alloc<bf16>((long long)B * T * cfg.joint_attention_dim);
+  pooled_in = alloc<bf16>((long long)B * cfg.pooled_projection_dim);
+  t_in = alloc<bf16>(B);
+  g_in = alloc<float>(B);
+  dt_dev = alloc<float>(4);
+  ids_txt = alloc<bf16>((long long)T * 3);
+  ids_img = alloc<bf16>((long long)S * 3);
+  tproj = alloc<bf16>((long long)B * 256);
+  h1 = alloc<bf16>((long long)B * D);
+  temb = alloc<bf16>((long long)B * D);
+  out_buf = alloc<bf16>((long long)B * S * cfg.out_channels);
+  lat_in = alloc<bf16>((long long)B * S * cfg.out_channels);
+  lat_out = alloc<bf16>((long long)B * S * cfg.out_channels);
+  rope = alloc<float2>((long long)N * (dh / 2));
+  CUDA_TRY(cudaMemset(cat, 0, R * 5 * D * sizeof(bf16)));
+
+  const long long rt = (long long)B * T, ri = (long long)B * S;
+  const long long row0[2] = {0, rt}, rows[2] = {rt, ri};
+  for (int g = 0; g < 2; ++g) {
+    mA_nbuf[g] = make_map_2d(err_, nbuf + row0[g] * D, rows[g], D, D, 128);
+    mA_attn[g] = make_map_2d(err_, cat + row0[g] * 5 * D, rows[g], D, 5LL * D, 128);
+    mA_mlp[g] = make_map_2d(err_, cat + row0[g] * 5 * D + D, rows[g], 4LL * D, 5LL * D, 128);
+    mA_cat[g] = make_map_2d(err_, cat + row0[g] * 5 * D, rows[g], 5LL * D, 5LL * D, 128);
+  }
+  mA_x = make_map_2d(err_, x_in, ri, cfg.in_channels, cfg.in_channels, 128);
+  mA_enc = make_map_2d(err_, enc_in, rt, cfg.joint_attention_dim, cfg.joint_attention_dim, 128);
+  mA_final = mA_nbuf[1];
+  mQ = make_map_3d(err_, q, (long long)B * H, N, dh);
+  mK = make_map_3d(err_, k, (long long)B * H, N, dh);
+  mV = make_map_3d(err_, v, (long long)B * H, N, dh);
+}
+
+// The launch sequence of one FluxTransformer2DModel.forward (+ optional fused Euler update).
+void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_noise_pred) {
+  const long long rt = (long long)B * T, ri = (long long)B * S;
+  const int L = cfg.num_layers, Ls = cfg.num_single_layers;
+  char nm[96];
+  auto name = [&](const char* fmt, int i, const char* suffix) {
+    snprintf(nm, sizeof nm, fmt, i);
+    return std::string(nm) + suffix;
+  };
+
+  // --- positional table (pos_embed(cat(txt_ids, img_ids)), transformer_flux.py:1114-1115)
+  {
+    RopeParams rp;
+    rp.txt_ids = ids_txt; rp.img_ids = ids_img; rp.T = T; rp.S = S;
+    rp.axes[0] = cfg.axes_dims_rope[0]; rp.axes[1] = cfg.axes_dims_rope[1]; rp.axes[2] = cfg.axes_dims_rope[2];
+    rp.half_dim = dh / 2; rp.out = rope;
+    const int total = N * (dh / 2);
+    rope_table_kernel<<<(total + 255) / 256, 256, 0, c.stream>>>(rp);
+    CUDA_TRY(cudaGetLastError());
+    ++*c.counter;
+  }
+  // --- temb = time_text_embed(timestep, guidance, pooled) (transformer_flux.py:1088-1098, embeddings.py:1327-1339)
+  {
+    timestep_embed_kernel<<<B, 128, 0, c.stream>>>(t_in, 0, B, tproj);
+    ++*c.counter;
+    launch_gemv(c, tproj, B, 256, W("t_embed.l1.w").ptr, W("t_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
+    launch_gemv(c, h1, B, D, W("t_embed.l2.w").ptr, W("t_embed.l2.b").ptr, D, temb, 0);
+    if (cfg.guidance_embeds) {
+      timestep_embed_kernel<<<B, 128, 0, c.stream>>>(g_in, 1, B, tproj);
+      ++*c.counter;
+      launch_gemv(c, tproj, B, 256, W("g_embed.l1.w").ptr, W("g_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
+      launch_gemv(c, h1, B, D, W("g_embed.l2.w").ptr, W("g_embed.l2.b").ptr, D, temb, GEMV_ADD_TO_OUT);
+    }
+    launch_gemv(c, pooled_in, B, cfg.pooled_projection_dim, W("p_embed.l1.w").ptr, W("p_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
+    launch_gemv(c, h1, B, D, W("p_embed.l2.w").ptr, W("p_embed.l2.b").ptr, D, temb, GEMV_ADD_TO_OUT);
+    CUDA_TRY(cudaGetLastError());
+  }
+  // --- every adaLN `linear(silu(temb))` of the step in one pass over the [mod_rows, D] matrix
+  launch_gemv(c, temb, B, D, W("mod.w").ptr, W("mod.b").ptr, mod_rows, mod, GEMV_PRE_SILU);
+
+  auto base_params = [&](int Nn, int Kk) {
+    GemmParams p;
+    memset(&p, 0, sizeof p);
+    p.N = Nn; p.K = Kk; p.num_groups = 2; p.n_split = Nn; p.mode0 = EPI_STORE; p.mode1 = EPI_STORE;
+    p.D = D; p.head_dim = dh; p.num_heads = H; p.n_joint = N; p.q = q; p.k = k; p.v = v; p.rope = rope;
+    p.rms_eps = 1e-6f; p.dt_ptr = dt_dev;
+    p.g[0].M = (int)rt; p.g[0].rows_per_sample = T; p.g[0].pos_offset = 0;
+    p.g[1].M = (int)ri; p.g[1].rows_per_sample = S; p.g[1].pos_offset = T;
+    return p;
+  };
+  // --- embedders (transformer_flux.py:1086,1099): text rows then image rows of `hidden`
+  {
+    GemmParams p = base_params(D, cfg.joint_attention_dim);
+    p.num_groups = 1;
+    p.g[0].bias = W("context_embedder.b").ptr; p.g[0].out = hidden; p.g[0].ldo = D;
+    launch_gemm(c, gemm_cta_group, mA_enc, mA_enc, WB("context_embedder.w"), WB("context_embedder.w"), p);
+    GemmParams px = base_params(D, cfg.in_channels);
+    px.num_groups = 1;
+    px.g[0] = px.g[1];
+    px.g[0].bias = W("x_embedder.b").ptr; px.g[0].out = hidden + rt * D; px.g[0].ldo = D;
+    launch_gemm(c, gemm_cta_group, mA_x, mA_x, WB("x_embedder.w"), WB("x_embedder.w"), px);
+  }
+  AttnParams ap;
+  ap.B = B; ap.H = H; ap.N = N; ap.T = T; ap.S = S;
+  ap.scale_log2 = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
+  ap.out = cat; ap.ld_out = 5LL * D;
+
+  LnModParams lp;
+  lp.x = hidden; lp.y = nbuf; lp.rows = (int)(rt + ri); lp.D = D; lp.row_begin = 0; lp.rows0 = (int)rt;
+  lp.rows_per0 = T; lp.rows_per1 = S; lp.mod = mod; lp.mod_stride = mod_rows; lp.eps = 1e-6f;
+
+  bf16* hid_g[2] = {hidden, hidden + rt * D};
+  bf16* cat_g[2] = {cat, cat + rt * 5 * D};
+
+  // --- 19 x FluxTransformerBlock (transformer_flux.py:794-841); chunk order shift,scale,gate (msa) shift,scale,gate (mlp)
+  for (int i = 0; i < L; ++i) {
+    const char* sfx[2] = {"_c", "_x"};
+    lp.shift0 = mod_double(i, 1, 0); lp.scale0 = mod_double(i, 1, 1);
+    lp.shift1 = mod_double(i, 0, 0); lp.scale1 = mod_double(i, 0, 1);
+    launch_ln_modulate(c, lp);
+    {
+      GemmParams p = base_params(3 * D, D);
+      p.mode0 = EPI_QKV;
+      for (int g = 0; g < 2; ++g) {
+        p.g[g].bias = W(name("d%d.qkv", i, sfx[g]) + ".b").ptr;
+        p.g[g].rms_q = W(name("d%d.rms_q", i, sfx[g])).ptr;
+        p.g[g].rms_k = W(name("d%d.rms_k", i, sfx[g])).ptr;
+      }
+      launch_gemm(c, gemm_cta_group, mA_nbuf[0], mA_nbuf[1], WB(name("d%d.qkv_c", i, ".w")), WB(name("d%d.qkv_x", i, ".w")), p);
+    }
+    launch_attention(c, dh, attn_q_tiles, mQ, mK, mV, ap);
+    {
+      GemmParams p = base_params(D, D);
+      p.mode0 = EPI_GATE_RES;
+      for (int g = 0; g < 2; ++g) {
+        p.g[g].bias = W(name("d%d.out", i, sfx[g]) + ".b").ptr;
+        p.g[g].out = hid_g[g]; p.g[g].ldo = D; p.g[g].res = hid_g[g]; p.g[g].ldr = D;
+        p.g[g].gate = mod + mod_double(i, g == 0, 2); p.g[g].gate_stride = mod_rows;
+      }
+      launch_gemm(c, gemm_cta_group, mA_attn[0], mA_attn[1], WB(name("d%d.out_c", i, ".w")), WB(name("d%d.out_x", i, ".w")), p);
+    }
+    lp.shift0 = mod_double(i, 1, 3); lp.scale0 = mod_double(i, 1, 4);
+    lp.shift1 = mod_double(i, 0, 3); lp.scale1 = mod_double(i, 0, 4);
+    launch_ln_modulate(c, lp);
+    {
+      GemmParams p = base_params(4 * D, D);
+      p.mode0 = EPI_GELU;
+      for (int g = 0; g < 2; ++g) {
+        p.g[g].bias = W(name("d%d.ff1", i, sfx[g]) + ".b").ptr;
+        p.g[g].out = cat_g[g] + D; p.g[g].ldo = 5LL * D;
+      }
+      launch_gemm(c, gemm_cta_group, mA_nbuf[0], mA_nbuf[1], WB(name("d%d.ff1_c", i, ".w")), WB(name("d%d.ff1_x", i, ".w")), p);
+    }
+    {
+      GemmParams p = base_params(D, 4 * D);
+      p.mode0 = EPI_GATE_RES;
+      for (int g = 0; g < 2; ++g) {
+        p.g[g].bias = W(name("d%d.ff2", i, sfx[g]) + ".b").ptr;
+        p.g[g].out = hid_g[g]; p.g[g].ldo = D; p.g[g].res = hid_g[g]; p.g[g].ldr = D;
+        p.g[g].gate = mod + mod_double(i, g == 0, 5); p.g[g].gate_stride = mod_rows;
+      }
+      launch_gemm(c, gemm_cta_group, mA_mlp[0], mA_mlp[1], WB(name("d%d.ff2_c", i, ".w")), WB(name("d%d.ff2_x", i, ".w")), p);
+    }
+  }
+  // --- 38 x FluxSingleTransformerBlock (transformer_flux.py:715-739) on the joint [text;image] rows (the cat of
+  //     :1160 is the row layout of `hidden` itself); chunk order shift, scale, gate
+  for (int j = 0; j < Ls; ++j) {
+    lp.shift0 = lp.shift1 = mod_single(j, 0);
+    lp.scale0 = lp.scale1 = mod_single(j, 1);
+    launch_ln_modulate(c, lp);
+    {
+      GemmParams p = base_params(7 * D, D);
+      p.n_split = 3 * D; p.mode0 = EPI_QKV; p.mode1 = EPI_GELU; p.col_offset1 = D;
+      for (int g = 0; g < 2; ++g) {
+        p.g[g].bias = W(name("s%d.qkvmlp", j, ".b")).ptr;
+        p.g[g].rms_q = W(name("s%d.rms_q", j, "")).ptr;
+        p.g[g].rms_k = W(name("s%d.rms_k", j, "")).ptr;
+        p.g[g].out = cat_g[g]; p.g[g].ldo = 5LL * D;
+      }
+      const CUtensorMap& wb = WB(name("s%d.qkvmlp", j, ".w"));
+      launch_gemm(c, gemm_cta_group, mA_nbuf[0], mA_nbuf[1], wb, wb, p);
+    }
+    launch_attention(c, dh, attn_q_tiles, mQ, mK, mV, ap);
+    {
+      GemmParams p = base_params(D, 5 * D);
+      p.mode0 = EPI_GATE_RES;
+      for (int g = 0; g < 2; ++g) {
+        p.g[g].bias = W(name("s%d.out", j, ".b")).ptr;
+        p.g[g].out = hid_g[g]; p.g[g].ldo = D; p.g[g].res = hid_g[g]; p.g[g].ldr = D;
+        p.g[g].gate = mod + mod_single(j, 2); p.g[g].gate_stride = mod_rows;
+      }
+      const CUtensorMap& wb = WB(name("s%d.out", j, ".w"));
+      launch_gemm(c, gemm_cta_group, mA_cat[0], mA_cat[1], wb, wb, p);
+    }
+  }
+  // --- norm_out (AdaLayerNormContinuous: chunk order scale, shift) + proj_out on the image rows (:1200-1203)
+  lp.row_begin = (int)rt;
+  lp.shift1 = mod_final(1); lp.scale1 = mod_final(0);
+  launch_ln_modulate(c, lp);
+  {
+    const int C = cfg.out_channels;
+    GemmParams p = base_params(C, D);
+    p.num_groups = 1;
+    p.g[0] = p.g[1];
+    p.g[0].bias = W("proj_out.b").ptr;
+    if (fused_euler) {
+      p.mode0 = EPI_EULER;
+      p.g[0].out = want_noise_pred ? out_buf : nullptr; p.g[0].ldo = C;
+      p.g[0].res = lat_in; p.g[0].ldr = C; p.g[0].out2 = lat_out;
+    } else {
+      p.g[0].out = out_buf; p.g[0].ldo = C;
+    }
+    launch_gemm(c, gemm_cta_group, mA_final, mA_final, WB("proj_out.w"), WB("proj_out.w"), p);
+  }
+}
+
+void tfx_model::run(bool fused_euler, bool want_noise_pred) {
+  LaunchCtx c{stream, device, &launches, err_};
+  cudaGraphExec_t& exec = fused_euler ? graph_step : graph_fwd;
+  if (!use_graph) {
+    enqueue_forward(c, fused_euler, want_noise_pred);
+    return;
+  }
+  if (!exec) {
+    long long scratch = 0;
+    LaunchCtx cc{stream, device, &scratch, err_};
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      enqueue_forward(cc, fused_euler, true);
+    } catch (...) {
+      cudaStreamEndCapture(stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    CUDA_TRY(cudaStreamEndCapture(stream, &graph));
+    CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    graph_nodes = scratch;
+  }
+  CUDA_TRY(cudaGraphLaunch(exec, stream));
+  launches += graph_nodes;
+}
+
+// ==================================================================================================== C ABI
+#define API_BEGIN(h)                       \
+  std::string* err_ = (h) ? &(h)->err : nullptr; \
+  (void)err_;                              \
+  try {
+#define API_END                                                    \
+  }                                                                \
+  catch (const Fail& f) { return f.code; }                         \
+  catch (const std::exception& e) { return set_error(err_, TFX_ERR_INVALID, "%s", e.what()); } \
+  return TFX_OK;
+
+extern "C" {
+
+const char* tfx_last_error(tfx_handle h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(cfg && out, TFX_ERR_INVALID, "null argument");
+    REQUIRE(cfg->attention_head_dim == 64 || cfg->attention_head_dim == 128, TFX_ERR_INVALID,
+            "attention_head_dim %d unsupported (64 or 128)", cfg->attention_head_dim);
+    const int D = cfg->attention_head_dim * cfg->num_attention_heads;
+    REQUIRE(D % 256 == 0, TFX_ERR_INVALID, "inner dim %d must be a multiple of 256", D);
+    REQUIRE(cfg->axes_dims_rope[0] + cfg->axes_dims_rope[1] + cfg->axes_dims_rope[2] == cfg->attention_head_dim,
+            TFX_ERR_INVALID, "axes_dims_rope must sum to attention_head_dim");
+    REQUIRE(cfg->in_channels % 64 == 0 && cfg->joint_attention_dim % 64 == 0 && cfg->pooled_projection_dim % 8 == 0,
+            TFX_ERR_INVALID, "in_channels / joint_attention_dim must be multiples of 64, pooled_projection_dim of 8");
+    REQUIRE(cfg->out_channels % 8 == 0 && cfg->out_channels <= 256, TFX_ERR_INVALID, "out_channels %d unsupported", cfg->out_channels);
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    REQUIRE(device >= 0 && device < ndev, TFX_ERR_INVALID, "device %d not present (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    REQUIRE(prop.major == 10, TFX_ERR_INVALID, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    configure_kernels(err_);
+    tfx_model* m = new tfx_model();
+    m->cfg = *cfg;
+    m->device = device;
+    m->D = D;
+    m->H = cfg->num_attention_heads;
+    m->dh = cfg->attention_head_dim;
+    m->mod_rows = ((long long)cfg->num_layers * 12 + (long long)cfg->num_single_layers * 3 + 2) * D;
+    cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&m->ev_in, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&m->ev_out, cudaEventDisableTiming);
+    *out = m;
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+void tfx_destroy(tfx_handle h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->free_workspace();
+  cudaEventDestroy(h->ev_in);
+  cudaEventDestroy(h->ev_out);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
+  API_BEGIN(h)
+  REQUIRE(h && key, TFX_ERR_INVALID, "null argument");
+  std::string k(key);
+  if (k == "gemm_cta_group") {
+    REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "gemm_cta_group must be 1 or 2");
+    h->gemm_cta_group = (int)value;
+  } else if (k == "attn_q_tiles") {
+    REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
+    h->attn_q_tiles = (int)value;
+  } else if (k == "use_graph") {
+    h->use_graph = value != 0;
+  } else {
+    REQUIRE(false, TFX_ERR_INVALID, "unknown option '%s'", key);
+  }
+  if (h->graph_fwd) { cudaGraphExecDestroy(h->graph_fwd); h->graph_fwd = nullptr; }
+  if (h->graph_step) { cudaGraphExecDestroy(h->graph_step); h->graph_step = nullptr; }
+  API_END
+}
+
+int tfx_get_counter(tfx_handle h, const char* key, int64_t* value) {
+  API_BEGIN(h)
+  REQUIRE(h && key && value, TFX_ERR_INVALID, "null argument");
+  std::string k(key);
+  if (k == "launches") *value = h->launches;
+  else if (k == "graph_nodes") *value = h->graph_nodes;
+  else REQUIRE(false, TFX_ERR_INVALID, "unknown counter '%s'", key);
+  API_END
+}
+
+int tfx_set_weight(tfx_handle h, const char* name, const void* dev_ptr, int64_t rows, int64_t cols) {
+  API_BEGIN(h)
+  REQUIRE(h && name && dev_ptr, TFX_ERR_INVALID, "null argument");
+  REQUIRE(rows > 0 && cols > 0, TFX_ERR_INVALID, "weight '%s' has empty shape", name);
+  REQUIRE((reinterpret_cast<uintptr_t>(dev_ptr) & 15) == 0, TFX_ERR_INVALID, "weight '%s' is not 16-byte aligned", name);
+  Weight t;
+  t.ptr = reinterpret_cast<const bf16*>(dev_ptr);
+  t.rows = rows;
+  t.cols = cols;
+  h->w[name] = t;
+  h->finalized = false;
+  API_END
+}
+
+int tfx_finalize_weights(tfx_handle h) {
+  API_BEGIN(h)
+  REQUIRE(h, TFX_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const tfx_config& c = h->cfg;
+  const long long D = h->D;
+  auto need = [&](const std::string& n, long long rows, long long cols) {
+    const Weight& t = h->W(n);
+    REQUIRE(t.rows == rows && t.cols == cols, TFX_ERR_INVALID, "weight '%s' is [%lld,%lld], expected [%lld,%lld]", n.c_str(),
+            t.rows, t.cols, rows, cols);
+  };
+  auto lin = [&](const std::string& n, long long o, long long i) { need(n + ".w", o, i); need(n + ".b", 1, o); };
+  lin("x_embedder", D, c.in_channels);
+  lin("context_embedder", D, c.joint_attention_dim);
+  lin("t_embed.l1", D, 256); lin("t_embed.l2", D, D);
+  if (c.guidance_embeds) { lin("g_embed.l1", D, 256); lin("g_embed.l2", D, D); }
+  lin("p_embed.l1", D, c.pooled_projection_dim); lin("p_embed.l2", D, D);
+  lin("mod", h->mod_rows, D);
+  lin("proj_out", c.out_channels, D);
+  char b[64];
+  for (int i = 0; i < c.num_layers; ++i) {
+    for (const char* s : {"_x", "_c"}) {
+      snprintf(b, sizeof b, "d%d.", i);
+      std::string p(b);
+      lin(p + "qkv" + s, 3 * D, D); lin(p + "out" + s, D, D); lin(p + "ff1" + s, 4 * D, D); lin(p + "ff2" + s, D, 4 * D);
+      need(p + "rms_q" + s, 1, h->dh); need(p + "rms_k" + s, 1, h->dh);
+    }
+  }
+  for (int j = 0; j < c.num_single_layers; ++j) {
+    snprintf(b, sizeof b, "s%d.", j);
+    std::string p(b);
+    lin(p + "qkvmlp", 7 * D, D); lin(p + "out", D, 5 * D);
+    need(p + "rms_q", 1, h->dh); need(p + "rms_k", 1, h->dh);
+  }
+  h->build_weight_maps();
+  h->finalized = true;
+  API_END
+}
+
+int tfx_prepare(tfx_handle h, int32_t B, int32_t S, int32_t T) {
+  API_BEGIN(h)
+  REQUIRE(h, TFX_ERR_INVALID, "null handle");
+  CUDA_TRY(cudaSetDevice(h->device));
+  h->prepare(B, S, T);
+  API_END
+}
+
+static void stage_common(tfx_model* h, std::string* err_, const void* enc, const void* pooled, const void* t, const void* g,
+                         const void* img_ids, const void* txt_ids, cudaStream_t user) {
+  REQUIRE(h->B > 0, TFX_ERR_STATE, "tfx_prepare has not been called");
+  REQUIRE(enc && pooled && t && img_ids && txt_ids, TFX_ERR_INVALID, "null input pointer");
+  REQUIRE(!h->cfg.guidance_embeds || g, TFX_ERR_INVALID, "guidance is required when guidance_embeds is set");
+  CUDA_TRY(cudaEventRecord(h->ev_in, user));
+  CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in, 0));
+  cudaStream_t s = h->stream;
+  CUDA_TRY(cudaMemcpyAsync(h->enc_in, enc, (size_t)h->B * h->T * h->cfg.joint_attention_dim * 2, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->pooled_in, pooled, (size_t)h->B * h->cfg.pooled_projection_dim * 2, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->t_in, t, (size_t)h->B * 2, cudaMemcpyDeviceToDevice, s));
+  if (h->cfg.guidance_embeds) CUDA_TRY(cudaMemcpyAsync(h->g_in, g, (size_t)h->B * 4, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->ids_img, img_ids, (size_t)h->S * 3 * 2, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->ids_txt, txt_ids, (size_t)h->T * 3 * 2, cudaMemcpyDeviceToDevice, s));
+}
+
+static void finish(tfx_model* h, std::string* err_, cudaStream_t user) {
+  CUDA_TRY(cudaEventRecord(h->ev_out, h->stream));
+  CUDA_TRY(cudaStreamWaitEvent(user, h->ev_out, 0));
+}
+
+int tfx_forward(tfx_handle h, const void* hidden_states, const void* encoder_hidden_states, const void* pooled,
+                const void* timestep_bf16, const void* guidance_f32, const void* img_ids, const void* txt_ids,
+                void* out_sample, void* stream) {
+  API_BEGIN(h)
+  REQUIRE(h && hidden_states && out_sample, TFX_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+  stage_common(h, err_, encoder_hidden_states, pooled, timestep_bf16, guidance_f32, img_ids, txt_ids, user);
+  CUDA_TRY(cudaMemcpyAsync(h->x_in, hidden_states, (size_t)h->B * h->S * h->cfg.in_channels * 2, cudaMemcpyDeviceToDevice, h->stream));
+  h->run(false, true);
+  CUDA_TRY(cudaMemcpyAsync(out_sample, h->out_buf, (size_t)h->B * h->S * h->cfg.out_channels * 2, cudaMemcpyDeviceToDevice, h->stream));
+  finish(h, err_, user);
+  API_END
+}
+
+int tfx_step(tfx_handle h, const void* latents_in, const void* cond, const void* encoder_hidden_states, const void* pooled,
+             const void* timestep_bf16, const void* guidance_f32, const void* img_ids, const void* txt_ids, float sigma,
+             float sigma_next, void* latents_out, void* noise_pred_out, void* stream) {
+  API_BEGIN(h)
+  REQUIRE(h && latents_in && cond && latents_out, TFX_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+  stage_common(h, err_, encoder_hidden_states, pooled, timestep_bf16, guidance_f32, img_ids, txt_ids, user);
+  const int Cl = h->cfg.out_channels, Cc = h->cfg.in_channels - h->cfg.out_channels, Ci = h->cfg.in_channels;
+  const size_t rows = (size_t)h->B * h->S;
+  cudaStream_t s = h->stream;
+  // hidden_states = cat(latents, cond, dim=2) (pipeline_flux_fill.py:2085) as two strided copies into the staging tile
+  CUDA_TRY(cudaMemcpy2DAsync(h->x_in, (size_t)Ci * 2, latents_in, (size_t)Cl * 2, (size_t)Cl * 2, rows, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpy2DAsync(h->x_in + Cl, (size_t)Ci * 2, cond, (size_t)Cc * 2, (size_t)Cc * 2, rows, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->lat_in, latents_in, rows * Cl * 2, cudaMemcpyDeviceToDevice, s));
+  const float dt = __bfloat162float(__float2bfloat16_rn(sigma_next - sigma));
+  set_float_kernel<<<1, 1, 0, s>>>(h->dt_dev, dt);
+  ++h->launches;
+  h->run(true, noise_pred_out != nullptr);
+  CUDA_TRY(cudaMemcpyAsync(latents_out, h->lat_out, rows * Cl * 2, cudaMemcpyDeviceToDevice, s));
+  if (noise_pred_out) CUDA_TRY(cudaMemcpyAsync(noise_pred_out, h->out_buf, rows * Cl * 2, cudaMemcpyDeviceToDevice, s));
+  finish(h, err_, user);
+  API_END
+}
+
+int tfx_euler_step(const void* model_output, const void* sample, void* prev_sample, int64_t n, float sigma, float sigma_next,
+                   void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(model_output && sample && prev_sample && n >= 0, TFX_ERR_INVALID, "bad argument");
+    if (n == 0) return TFX_OK;
+    const float dt = __bfloat162float(__float2bfloat16_rn(sigma_next - sigma));
+    euler_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const bf16*>(model_output), reinterpret_cast<const bf16*>(sample), reinterpret_cast<bf16*>(prev_sample), n, dt);
+    CUDA_TRY(cudaGetLastError());
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ op-level entry points
+static long long g_op_launches = 0;
+
+int tfx_op_linear(const void* A, int64_t lda, const void* Wt, const void* bias, void* out, int64_t ldo, int32_t M, int32_t N,
+                  int32_t K, int32_t mode, const void* gate, const void* res, int32_t cta_group, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(A && Wt && bias && out, TFX_ERR_INVALID, "null argument");
+    REQUIRE(mode >= 0 && mode <= 2, TFX_ERR_INVALID, "mode must be 0..2");
+    REQUIRE(cta_group == 1 || cta_group == 2, TFX_ERR_INVALID, "cta_group must be 1 or 2");
+    REQUIRE(mode != EPI_GATE_RES || (gate && res), TFX_ERR_INVALID, "gate/res required for mode 2");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    configure_kernels(err_);
+    if (M == 0) return TFX_OK;
+    CUtensorMap ma = make_map_2d(err_, A, M, K, lda, 128);
+    CUtensorMap mb = make_map_2d(err_, Wt, N, K, K, kGemmBlockN / cta_group);
+    GemmParams p;
+    memset(&p, 0, sizeof p);
+    p.N = N; p.K = K; p.num_groups = 1; p.n_split = N; p.mode0 = mode; p.mode1 = mode;
+    p.g[0].M = M; p.g[0].rows_per_sample = M; p.g[0].bias = reinterpret_cast<const bf16*>(bias);
+    p.g[0].out = reinterpret_cast<bf16*>(out); p.g[0].ldo = ldo;
+    p.g[0].res = reinterpret_cast<const bf16*>(res); p.g[0].ldr = ldo;
+    p.g[0].gate = reinterpret_cast<const bf16*>(gate); p.g[0].gate_stride = 0;
+    LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
+    launch_gemm(c, cta_group, ma, ma, mb, mb, p);
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int64_t ld_out, int32_t B, int32_t H, int32_t T,
+                     int32_t S, int32_t head_dim, int32_t q_tiles, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(q && k && v && out, TFX_ERR_INVALID, "null argument");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    configure_kernels(err_);
+    const int N = T + S;
+    if (N == 0 || B == 0) return TFX_OK;
+    CUtensorMap mq = make_map_3d(err_, q, (long long)B * H, N, head_dim);
+    CUtensorMap mk = make_map_3d(err_, k, (long long)B * H, N, head_dim);
+    CUtensorMap mv = make_map_3d(err_, v, (long long)B * H, N, head_dim);
+    AttnParams p;
+    p.B = B; p.H = H; p.N = N; p.T = T; p.S = S;
+    p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
+    p.out = reinterpret_cast<bf16*>(out); p.ld_out = ld_out;
+    LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
+    launch_attention(c, head_dim, q_tiles, mq, mk, mv, p);
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+int tfx_op_ln_modulate(const void* x, void* y, int32_t rows, int32_t D, int32_t rows_per_sample, const void* mod,
+                       int64_t mod_stride, int64_t shift_off, int64_t scale_off, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(x && y && mod && rows_per_sample > 0, TFX_ERR_INVALID, "bad argument");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    LnModParams p;
+    p.x = reinterpret_cast<const bf16*>(x); p.y = reinterpret_cast<bf16*>(y); p.rows = rows; p.D = D; p.row_begin = 0;
+    p.rows0 = rows; p.rows_per0 = rows_per_sample; p.rows_per1 = rows_per_sample;
+    p.mod = reinterpret_cast<const bf16*>(mod); p.mod_stride = mod_stride;
+    p.shift0 = p.shift1 = shift_off; p.scale0 = p.scale1 = scale_off; p.eps = 1e-6f;
+    LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
+    launch_ln_modulate(c, p);
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+int tfx_op_gemv(const void* x, int32_t B, int32_t K, const void* Wt, const void* bias, int64_t N, void* out, int32_t flags,
+                void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(x && Wt && bias && out, TFX_ERR_INVALID, "null argument");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
+    launch_gemv(c, reinterpret_cast<const bf16*>(x), B, K, reinterpret_cast<const bf16*>(Wt), reinterpret_cast<const bf16*>(bias), N,
+                reinterpret_cast<bf16*>(out), flags);
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+int tfx_op_rope_table(const void* txt_ids, const void* img_ids, int32_t T, int32_t S, const int32_t* axes_dims, void* out_f32,
+                      void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(txt_ids && img_ids && axes_dims && out_f32, TFX_ERR_INVALID, "null argument");
+    RopeParams rp;
+    rp.txt_ids = reinterpret_cast<const bf16*>(txt_ids); rp.img_ids = reinterpret_cast<const bf16*>(img_ids);
+    rp.T = T; rp.S = S;
+    rp.axes[0] = axes_dims[0]; rp.axes[1] = axes_dims[1]; rp.axes[2] = axes_dims[2];
+    rp.half_dim = (axes_dims[0] + axes_dims[1] + axes_dims[2]) / 2;
+    rp.out = reinterpret_cast<float2*>(out_f32);
+    const int total = (T + S) * rp.half_dim;
+    if (total == 0) return TFX_OK;
+    rope_table_kernel<<<(total + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(rp);
+    CUDA_TRY(cudaGetLastError());
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+int tfx_op_timestep_embed(const void* t, int32_t is_f32, int32_t B, void* out, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(t && out && B > 0, TFX_ERR_INVALID, "bad argument");
+    timestep_embed_kernel<<<B, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, is_f32, B, reinterpret_cast<bf16*>(out));
+    CUDA_TRY(cudaGetLastError());
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+int tfx_op_umma_probe(const void* A, const void* Bm, void* D_f32, int32_t n_dim, int32_t k_dim, int32_t b_mn_major,
+                      int32_t a_from_tmem, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep_bytes, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(A && Bm && D_f32, TFX_ERR_INVALID, "null argument");
+    REQUIRE(k_dim % 64 == 0 && k_dim >= 64 && k_dim <= 256 && n_dim % 64 == 0 && n_dim >= 64 && n_dim <= 256, TFX_ERR_INVALID,
+            "probe supports n,k in {64,128,192,256}");
+    configure_kernels(err_);
+    CUtensorMap ma = make_map_2d(err_, A, 128, k_dim, k_dim, 128);
+    CUtensorMap mb = b_mn_major ? make_map_2d(err_, Bm, k_dim, n_dim, n_dim, k_dim) : make_map_2d(err_, Bm, n_dim, k_dim, k_dim, n_dim);
+    ProbeParams p;
+    p.A = reinterpret_cast<const bf16*>(A); p.D = reinterpret_cast<float*>(D_f32); p.n = n_dim; p.k = k_dim;
+    p.b_mn_major = b_mn_major; p.a_from_tmem = a_from_tmem; p.b_lbo = b_lbo; p.b_sbo = b_sbo; p.b_kstep_bytes = b_kstep_bytes;
+    umma_probe_kernel<<<1, 128, 200 * 1024, reinterpret_cast<cudaStream_t>(stream)>>>(ma, mb, p);
+    CUDA_TRY(cudaGetLastError());
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,389 @@
+"""Host-side mirror of the reference interface for the denoising hot path.
+
+`B200FluxTransformer` answers the calls FluxFillPipeline makes on `self.transformer`
+(pipeline_flux_fill.py:2069 `.config.guidance_embeds`, :2084-2094 `forward(...)`, :1660 `.dtype`;
+pipeline_utils.py:478-489 `.device`) and `B200FlowMatchEulerScheduler` those it makes on `self.scheduler`
+(:2053-2056 `.config.*`, :1305-1314 `set_timesteps(sigmas=, mu=)`, :2065 `.order`, :2077 `.timesteps`, :2098 `.step`).
+Everything below the call is the CUDA library behind include/textflux_b200.h; torch only owns device memory and
+the stream.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from types import SimpleNamespace
+from typing import Callable, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .packer import pack_weights
+
+Tensor = torch.Tensor
+
+
+class FrozenConfig(dict):
+    """dict with attribute access, like diffusers' FrozenDict (configuration_utils.py:55-62)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+    def __setattr__(self, k, v):
+        raise AttributeError("config is frozen")
+
+
+def _cfg_dict(cfg) -> dict:
+    keys = ("patch_size", "in_channels", "out_channels", "num_layers", "num_single_layers", "attention_head_dim",
+            "num_attention_heads", "joint_attention_dim", "pooled_projection_dim", "guidance_embeds", "axes_dims_rope")
+    get = (lambda k: cfg[k]) if isinstance(cfg, dict) else (lambda k: getattr(cfg, k))
+    d = {k: get(k) for k in keys}
+    if d["out_channels"] is None:
+        d["out_channels"] = d["in_channels"]
+    d["axes_dims_rope"] = tuple(d["axes_dims_rope"])
+    if d["patch_size"] != 1:
+        raise ValueError("textflux_b200: patch_size must be 1 (FLUX packs 2x2 patches in the pipeline)")
+    if len(d["axes_dims_rope"]) != 3:
+        raise ValueError("textflux_b200: axes_dims_rope must have 3 entries")
+    return d
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Transformer2DModelOutput(SimpleNamespace):
+    """Mirror of models/modeling_outputs.py Transformer2DModelOutput (attribute `sample`)."""
+
+
+class B200FluxTransformer(torch.nn.Module):
+    """Drop-in for FluxTransformer2DModel (transformer_flux.py:844-1212) on one B200.
+
+    Build it from a loaded reference module (`from_reference`) or from any `get(name) -> tensor` source of the
+    reference state dict (`from_getter`), then assign it to `pipe.transformer`.
+    """
+
+    def __init__(self, config, get: Callable[[str], Tensor], device: Union[str, torch.device] = "cuda",
+                 gemm_cta_group: Optional[int] = None, attn_q_tiles: Optional[int] = None, use_graph: bool = True):
+        super().__init__()
+        self._lib = _lib.load()
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("textflux_b200 runs on CUDA (sm_100a) devices only; there is no CPU path")
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self.config = FrozenConfig(_cfg_dict(config))
+        self._dev = dev
+        c = self.config
+        tc = _lib.TfxConfig(c.in_channels, c.out_channels, c.num_layers, c.num_single_layers, c.attention_head_dim,
+                            c.num_attention_heads, c.joint_attention_dim, c.pooled_projection_dim,
+                            int(bool(c.guidance_embeds)), (C.c_int32 * 3)(*c.axes_dims_rope))
+        h = C.c_void_p()
+        _lib.check(self._lib.tfx_create(C.byref(tc), dev.index, C.byref(h)))
+        self._h = h
+        self.register_buffer("_anchor", torch.zeros(1, dtype=torch.bfloat16, device=dev), persistent=False)
+        with torch.cuda.device(dev):
+            self._weights: Dict[str, Tensor] = pack_weights(SimpleNamespace(**c), get, dev, torch.bfloat16)
+        for name, t in self._weights.items():
+            _lib.check(self._lib.tfx_set_weight(self._h, name.encode(), t.data_ptr(), t.shape[0], t.shape[1]), self._h)
+        _lib.check(self._lib.tfx_finalize_weights(self._h), self._h)
+        if gemm_cta_group is not None:
+            self.set_option("gemm_cta_group", gemm_cta_group)
+        if attn_q_tiles is not None:
+            self.set_option("attn_q_tiles", attn_q_tiles)
+        self.set_option("use_graph", int(use_graph))
+        self._shape: Optional[Tuple[int, int, int]] = None
+
+    # ---- construction helpers -------------------------------------------------------------------------------
+    @classmethod
+    def from_reference(cls, module: torch.nn.Module, device="cuda", **kw) -> "B200FluxTransformer":
+        """`module` is a loaded reference FluxTransformer2DModel (weights + `.config`); it can be freed afterwards."""
+        sd = module.state_dict()
+        return cls(module.config, sd.__getitem__, device=device, **kw)
+
+    @classmethod
+    def from_state_dict(cls, config, state_dict: Dict[str, Tensor], device="cuda", **kw) -> "B200FluxTransformer":
+        return cls(config, state_dict.__getitem__, device=device, **kw)
+
+    # ---- what DiffusionPipeline reads -------------------------------------------------------------------------
+    @property
+    def device(self) -> torch.device:
+        return self._dev
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return torch.bfloat16
+
+    def to(self, *args, **kwargs):
+        """The engine is bound to its device at construction; `.to()` with the same device/dtype is a no-op."""
+        dev, dtype, _, _ = torch._C._nn._parse_to(*args, **kwargs)
+        if dev is not None and torch.device(dev).type != "cuda":
+            raise RuntimeError("textflux_b200: the engine cannot leave its CUDA device (no CPU path)")
+        if dev is not None and torch.device(dev).index not in (None, self._dev.index):
+            raise RuntimeError(f"textflux_b200: engine lives on {self._dev}; build a new one for {dev}")
+        if dtype is not None and dtype != torch.bfloat16:
+            raise RuntimeError("textflux_b200: the engine computes in bf16 only")
+        return self
+
+    def set_option(self, key: str, value: int) -> None:
+        _lib.check(self._lib.tfx_set_option(self._h, key.encode(), int(value)), self._h)
+
+    def counter(self, key: str) -> int:
+        v = C.c_int64()
+        _lib.check(self._lib.tfx_get_counter(self._h, key.encode(), C.byref(v)), self._h)
+        return v.value
+
+    def __del__(self):
+        h, lib = getattr(self, "_h", None), getattr(self, "_lib", None)
+        if h and lib:
+            lib.tfx_destroy(h)
+            self._h = None
+
+    # ---- helpers ------------------------------------------------------------------------------------------------
+    def _prepare(self, B: int, S: int, T: int) -> None:
+        if self._shape != (B, S, T):
+            _lib.check(self._lib.tfx_prepare(self._h, B, S, T), self._h)
+            self._shape = (B, S, T)
+
+    def _bf16(self, t: Tensor, name: str, shape: Tuple[int, ...]) -> Tensor:
+        if t is None:
+            raise ValueError(f"textflux_b200: `{name}` is required")
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"textflux_b200: `{name}` has shape {tuple(t.shape)}, expected {tuple(shape)}")
+        if t.device != self._dev:
+            raise ValueError(f"textflux_b200: `{name}` is on {t.device}, the engine on {self._dev}")
+        return t.to(torch.bfloat16).contiguous()
+
+    def _ids(self, ids: Tensor, name: str, n: int) -> Tensor:
+        if ids.ndim == 3:  # deprecated batched ids (transformer_flux.py:1100-1113)
+            ids = ids[0]
+        return self._bf16(ids, name, (n, 3))
+
+    # ---- FluxTransformer2DModel.forward (transformer_flux.py:1028-1212) -------------------------------------------
+    @torch.no_grad()
+    def forward(self, hidden_states: Tensor, encoder_hidden_states: Tensor = None, pooled_projections: Tensor = None,
+                timestep: Tensor = None, img_ids: Tensor = None, txt_ids: Tensor = None, guidance: Tensor = None,
+                joint_attention_kwargs: Optional[dict] = None, controlnet_block_samples=None,
+                controlnet_single_block_samples=None, return_dict: bool = True, controlnet_blocks_repeat: bool = False):
+        if controlnet_block_samples is not None or controlnet_single_block_samples is not None:
+            raise ValueError("textflux_b200: controlnet residuals are not part of the TextFlux path")
+        if hidden_states.ndim != 3:
+            raise ValueError("textflux_b200: hidden_states must be [B, S, in_channels]")
+        c = self.config
+        B, S, _ = hidden_states.shape
+        T = encoder_hidden_states.shape[1]
+        out_dtype = hidden_states.dtype
+        hs = self._bf16(hidden_states, "hidden_states", (B, S, c.in_channels))
+        enc = self._bf16(encoder_hidden_states, "encoder_hidden_states", (B, T, c.joint_attention_dim))
+        pooled = self._bf16(pooled_projections, "pooled_projections", (B, c.pooled_projection_dim))
+        t = self._bf16(timestep, "timestep", (B,))
+        g = None
+        if c.guidance_embeds:
+            if guidance is None:
+                raise ValueError("textflux_b200: `guidance` is required when config.guidance_embeds is set")
+            g = guidance.to(device=self._dev, dtype=torch.float32).expand(B).contiguous()
+        img = self._ids(img_ids, "img_ids", S)
+        txt = self._ids(txt_ids, "txt_ids", T)
+        out = torch.empty(B, S, c.out_channels, dtype=torch.bfloat16, device=self._dev)
+        with torch.cuda.device(self._dev):
+            self._prepare(B, S, T)
+            stream = torch.cuda.current_stream(self._dev).cuda_stream
+            _lib.check(self._lib.tfx_forward(self._h, hs.data_ptr(), enc.data_ptr(), pooled.data_ptr(), t.data_ptr(),
+                                             _ptr(g), img.data_ptr(), txt.data_ptr(), out.data_ptr(), stream), self._h)
+        out = out.to(out_dtype)
+        if not return_dict:
+            return (out,)
+        return Transformer2DModelOutput(sample=out)
+
+    # ---- one fused sampling step: pipeline_flux_fill.py:2082-2098 ---------------------------------------------------
+    @torch.no_grad()
+    def step(self, latents: Tensor, cond: Tensor, encoder_hidden_states: Tensor, pooled_projections: Tensor,
+             timestep: Tensor, guidance: Optional[Tensor], img_ids: Tensor, txt_ids: Tensor, sigma: float,
+             sigma_next: float, return_noise_pred: bool = False):
+        """latents' = scheduler.step(transformer(cat(latents, cond), ...), t, latents), the Euler update fused into the
+        last GEMM's store.  `timestep` is t/1000 in bf16 as the pipeline would pass it."""
+        c = self.config
+        B, S, _ = latents.shape
+        T = encoder_hidden_states.shape[1]
+        lat = self._bf16(latents, "latents", (B, S, c.out_channels))
+        cnd = self._bf16(cond, "cond", (B, S, c.in_channels - c.out_channels))
+        enc = self._bf16(encoder_hidden_states, "encoder_hidden_states", (B, T, c.joint_attention_dim))
+        pooled = self._bf16(pooled_projections, "pooled_projections", (B, c.pooled_projection_dim))
+        t = self._bf16(timestep, "timestep", (B,))
+        g = guidance.to(device=self._dev, dtype=torch.float32).expand(B).contiguous() if c.guidance_embeds else None
+        img = self._ids(img_ids, "img_ids", S)
+        txt = self._ids(txt_ids, "txt_ids", T)
+        out = torch.empty_like(lat)
+        pred = torch.empty_like(lat) if return_noise_pred else None
+        with torch.cuda.device(self._dev):
+            self._prepare(B, S, T)
+            stream = torch.cuda.current_stream(self._dev).cuda_stream
+            _lib.check(self._lib.tfx_step(self._h, lat.data_ptr(), cnd.data_ptr(), enc.data_ptr(), pooled.data_ptr(),
+                                          t.data_ptr(), _ptr(g), img.data_ptr(), txt.data_ptr(), float(sigma),
+                                          float(sigma_next), out.data_ptr(), _ptr(pred), stream), self._h)
+        return (out, pred) if return_noise_pred else out
+
+    @torch.no_grad()
+    def denoise(self, latents: Tensor, cond: Tensor, prompt_embeds: Tensor, pooled_prompt_embeds: Tensor,
+                txt_ids: Tensor, img_ids: Tensor, guidance_scale: float, num_inference_steps: int,
+                scheduler: Optional["B200FlowMatchEulerScheduler"] = None,
+                callback: Optional[Callable[[int, Tensor], None]] = None) -> Tensor:
+        """The whole loop of FluxFillPipeline.__call__ (pipeline_flux_fill.py:2049-2119): schedule, then one fused
+        step per timestep.  Returns the final packed latents."""
+        sch = scheduler or B200FlowMatchEulerScheduler()
+        S = latents.shape[1]
+        mu = calculate_shift(S, sch.config.base_image_seq_len, sch.config.max_image_seq_len, sch.config.base_shift,
+                             sch.config.max_shift)
+        sch.set_timesteps(sigmas=np.linspace(1.0, 1 / num_inference_steps, num_inference_steps), device=self._dev, mu=mu)
+        B = latents.shape[0]
+        guidance = torch.full([1], guidance_scale, device=self._dev, dtype=torch.float32).expand(B) \
+            if self.config.guidance_embeds else None
+        # timestep = t.expand(B).to(latents.dtype); transformer(timestep / 1000)   (:2082,2086)
+        ts = (sch.timesteps.to(self._dev)[:, None].expand(-1, B).to(latents.dtype) / 1000).contiguous()
+        sig = sch.sigmas_cpu
+        for i in range(len(sch.timesteps)):
+            latents = self.step(latents, cond, prompt_embeds, pooled_prompt_embeds, ts[i], guidance, img_ids, txt_ids,
+                                sig[i], sig[i + 1])
+            if callback is not None:
+                callback(i, latents)
+        return latents
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def calculate_shift(image_seq_len, base_seq_len: int = 256, max_seq_len: int = 4096, base_shift: float = 0.5,
+                    max_shift: float = 1.16) -> float:
+    """pipeline_flux_fill.py:1248-1258 (same default arguments)."""
+    m = (max_shift - base_shift) / (max_seq_len - base_seq_len)
+    b = base_shift - m * base_seq_len
+    return image_seq_len * m + b
+
+
+class B200FlowMatchEulerScheduler:
+    """Drop-in for FlowMatchEulerDiscreteScheduler (scheduling_flow_match_euler_discrete.py:33-338) on the FLUX path:
+    same config keys, same `set_timesteps` arithmetic (numpy float32 sigmas, dynamic time shift), same step-index
+    bookkeeping; `step` runs the fused CUDA update instead of four eager kernels."""
+
+    order = 1
+
+    def __init__(self, num_train_timesteps: int = 1000, shift: float = 1.0, use_dynamic_shifting: bool = True,
+                 base_shift: float = 0.5, max_shift: float = 1.15, base_image_seq_len: int = 256,
+                 max_image_seq_len: int = 4096):
+        self.config = FrozenConfig(num_train_timesteps=num_train_timesteps, shift=shift,
+                                   use_dynamic_shifting=use_dynamic_shifting, base_shift=base_shift,
+                                   max_shift=max_shift, base_image_seq_len=base_image_seq_len,
+                                   max_image_seq_len=max_image_seq_len)
+        ts = np.linspace(1, num_train_timesteps, num_train_timesteps, dtype=np.float32)[::-1].copy()
+        sig = torch.from_numpy(ts).to(torch.float32) / num_train_timesteps
+        if not use_dynamic_shifting:
+            sig = shift * sig / (1 + (shift - 1) * sig)
+        self.timesteps = sig * num_train_timesteps
+        self.sigmas = sig.to("cpu")
+        self.sigmas_cpu: List[float] = self.sigmas.tolist()
+        self.sigma_min = self.sigmas[-1].item()
+        self.sigma_max = self.sigmas[0].item()
+        self._timesteps_cpu = self.timesteps.clone()
+        self._step_index: Optional[int] = None
+        self._begin_index: Optional[int] = None
+        self.num_inference_steps: Optional[int] = None
+
+    @classmethod
+    def from_config(cls, config) -> "B200FlowMatchEulerScheduler":
+        get = (lambda k, d: config.get(k, d)) if isinstance(config, dict) else (lambda k, d: getattr(config, k, d))
+        return cls(get("num_train_timesteps", 1000), get("shift", 1.0), get("use_dynamic_shifting", True),
+                   get("base_shift", 0.5), get("max_shift", 1.15), get("base_image_seq_len", 256),
+                   get("max_image_seq_len", 4096))
+
+    @property
+    def step_index(self):
+        return self._step_index
+
+    @property
+    def begin_index(self):
+        return self._begin_index
+
+    def set_begin_index(self, begin_index: int = 0):
+        self._begin_index = begin_index
+
+    def time_shift(self, mu: float, sigma: float, t):
+        return math.exp(mu) / (math.exp(mu) + (1 / t - 1) ** sigma)
+
+    def set_timesteps(self, num_inference_steps: int = None, device=None, sigmas=None, mu: Optional[float] = None):
+        """scheduling_flow_match_euler_discrete.py:184-241."""
+        if self.config.use_dynamic_shifting and mu is None:
+            raise ValueError(" you have a pass a value for `mu` when `use_dynamic_shifting` is set to be `True`")
+        n_train = self.config.num_train_timesteps
+        if sigmas is None:
+            timesteps = np.linspace(self.sigma_max * n_train, self.sigma_min * n_train, num_inference_steps)
+            sigmas = timesteps / n_train
+        else:
+            sigmas = np.array(sigmas).astype(np.float32)
+            num_inference_steps = len(sigmas)
+        self.num_inference_steps = num_inference_steps
+        if self.config.use_dynamic_shifting:
+            sigmas = self.time_shift(mu, 1.0, sigmas)
+        else:
+            sigmas = self.config.shift * sigmas / (1 + (self.config.shift - 1) * sigmas)
+        sig = torch.from_numpy(np.asarray(sigmas)).to(dtype=torch.float32)
+        ts = sig * n_train
+        sig = torch.cat([sig, torch.zeros(1)])
+        self._timesteps_cpu = ts.clone()
+        self.sigmas_cpu = sig.tolist()
+        self.timesteps = ts.to(device=device)
+        self.sigmas = sig.to(device=device)
+        self._step_index = None
+        self._begin_index = None
+
+    def index_for_timestep(self, timestep, schedule_timesteps=None):
+        st = self._timesteps_cpu if schedule_timesteps is None else schedule_timesteps.detach().to("cpu")
+        t = float(timestep.detach().to("cpu", torch.float32)) if isinstance(timestep, torch.Tensor) else float(timestep)
+        idx = (st == t).nonzero()
+        pos = 1 if len(idx) > 1 else 0
+        return idx[pos].item()
+
+    def _init_step_index(self, timestep):
+        self._step_index = self.index_for_timestep(timestep) if self._begin_index is None else self._begin_index
+
+    @torch.no_grad()
+    def step(self, model_output: Tensor, timestep, sample: Tensor, s_churn: float = 0.0, s_tmin: float = 0.0,
+             s_tmax: float = float("inf"), s_noise: float = 1.0, generator=None, return_dict: bool = True):
+        """scheduling_flow_match_euler_discrete.py:265-338."""
+        if isinstance(timestep, int) or (isinstance(timestep, torch.Tensor)
+                                         and timestep.dtype in (torch.int32, torch.int64)):
+            raise ValueError("Passing integer indices (e.g. from `enumerate(timesteps)`) as timesteps to"
+                             " `EulerDiscreteScheduler.step()` is not supported. Make sure to pass"
+                             " one of the `scheduler.timesteps` as a timestep.")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        if model_output.device.type != "cuda":
+            raise RuntimeError("textflux_b200: scheduler.step runs on CUDA tensors only (no CPU path)")
+        if model_output.dtype != torch.bfloat16 or model_output.shape != sample.shape:
+            raise ValueError("textflux_b200: scheduler.step expects bf16 model_output with sample's shape")
+        sigma, sigma_next = self.sigmas_cpu[self._step_index], self.sigmas_cpu[self._step_index + 1]
+        v = model_output.contiguous()
+        x = sample.to(torch.bfloat16).contiguous()
+        out = torch.empty_like(v)
+        lib = _lib.load()
+        with torch.cuda.device(v.device):
+            stream = torch.cuda.current_stream(v.device).cuda_stream
+            _lib.check(lib.tfx_euler_step(v.data_ptr(), x.data_ptr(), out.data_ptr(), v.numel(), float(sigma),
+                                          float(sigma_next), stream))
+        self._step_index += 1
+        if not return_dict:
+            return (out,)
+        return SimpleNamespace(prev_sample=out)
+
+    def __len__(self):
+        return self.config.num_train_timesteps
+
+
+def attach(pipe, **engine_kw):
+    """Swap the engine into a loaded reference FluxFillPipeline in place (zero edits to reference files):
+    `pipe.transformer` -> B200FluxTransformer built from the loaded weights, `pipe.scheduler` -> fused scheduler."""
+    eng = B200FluxTransformer.from_reference(pipe.transformer, device=pipe.transformer.device, **engine_kw)
+    sch = B200FlowMatchEulerScheduler.from_config(pipe.scheduler.config)
+    pipe.transformer = eng
+    pipe.scheduler = sch
+    return pipe
