@@ -88,7 +88,7 @@ SHAPES = [(128, 256, 64), (256, 512, 384), (2560, 3072, 3072), (512, 3072, 4096)
           (200, 768, 1280), (2048, 12288, 3072), (2048, 3072, 15360), (300, 320, 192)]
 
 
-@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_linear_store(lib, M, N, K, cta_group):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
@@ -101,7 +101,7 @@ def test_linear_store(lib, M, N, K, cta_group):
     assert err < 4e-3, err  # bf16 output rounding ~ 2^-9 relative
 
 
-@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
 def test_linear_gelu_and_gate_res(lib, cta_group):
     M, N, K = 384, 1024, 256
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -152,7 +152,7 @@ def _attention(lib, q, k, v, T, q_tiles):
     return torch.cat([txt, img], dim=1)
 
 
-@pytest.mark.parametrize("q_tiles", [1, 2])
+@pytest.mark.parametrize("q_tiles", [1, 2], ids=["qt1", "qt2"])
 @pytest.mark.parametrize("B,H,T,S,dh", [(1, 2, 128, 128, 128), (1, 24, 512, 2048, 128), (2, 4, 16, 64, 64), (1, 3, 40, 217, 128),
                                           (2, 2, 100, 412, 64), (1, 1, 0, 128, 128)])
 def test_attention(lib, B, H, T, S, dh, q_tiles):
