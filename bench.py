@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Headline benchmark: denoising-steps/sec (device-timed) of the FLUX-Fill 12B hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic input: FluxTransformer2DModel.forward on
+cat(latents, cond) + FlowMatchEulerDiscreteScheduler.step, i.e. the loop body of pipeline_flux_fill.py:2082-2098.
+Workload at N=1: BASELINE.json configs[1] (FLUX.1-Fill-dev 12B, 512x512 scene + full-mask glyph concat -> 1024x512
+canvas, S=2048 image tokens, T=512 text tokens, batch 1, bf16).  Multi-GPU: weight replicas, one sample per rank, one
+NCCL broadcast of the prompt embeddings + sigma schedule before the loop, no per-step collective ("weak" scaling).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # name -> (canvas h2 x w2 packed tokens, T, description)
+    "cfg2": (64, 32, 512, "FLUX.1-Fill-dev 12B, 512x512 scene + full-mask glyph concat (1024x512 canvas, S=2048, T=512)"),
+    "cfg3": (72, 64, 512, "TextFlux-beta strip: 1024x1024 scene + 128-px glyph strip (1152x1024 canvas, S=4608, T=512)"),
+    "cfg4": (64, 64, 512, "LoRA r16 folded, 1024x1024 (S=4096, T=512)"),
+    "cfg5": (128, 64, 512, "multi-line full-mask 1024x2048 concat (S=8192, T=512)"),
+}
+METRIC = "denoising-steps/sec (device-timed) FLUX-Fill 12B"
+UNIT = "steps/s"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(burst=float(p["bf16_tflops"]), sustained=float(p["bf16_tflops_sustained"]), hbm=float(p["hbm_gbs"]),
+                    source="MEASURED_PEAKS.json (measured)")
+    except Exception:
+        return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="B200_PROFILING.md fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+_CPU_CACHE = {}
+
+
+def cpu_reference_sample(h2, w2, T, reps=1):
+    """The reference's CPU path on this box's host cores, bounded sample: 1 double + 1 single block of the real
+    12B dims at the workload's shape, timed and scaled by the block counts (19 / 38).  Uses the oracle port of the
+    reference forward (bit-exact to the reference on CPU, tests/test_oracle_golden.py)."""
+    from oracle import flux_oracle as fo
+    cfg = fo.FluxConfig(num_layers=1, num_single_layers=1)
+    torch.set_num_threads(os.cpu_count() or 1)
+    if "sd" not in _CPU_CACHE:
+        _CPU_CACHE["sd"] = fo.init_state_dict(cfg, seed=7, dtype=torch.bfloat16)
+    sd = _CPU_CACHE["sd"]
+    S = h2 * w2
+    g = torch.Generator().manual_seed(0)
+    D = cfg.inner_dim
+    x = torch.randn(1, S, D, generator=g).to(torch.bfloat16)
+    enc = torch.randn(1, T, D, generator=g).to(torch.bfloat16)
+    temb = torch.randn(1, D, generator=g).to(torch.bfloat16)
+    ids = torch.cat([torch.zeros(T, 3), fo.prepare_latent_image_ids(h2, w2, torch.float32)])
+    rope = fo.flux_pos_embed(ids, cfg.axes_dims_rope)
+    full = fo.FLUX_FILL_12B
+    with torch.no_grad():
+        fo.double_block(sd, 0, cfg, x, enc, temb, rope)  # warm-up (thread pool, allocator)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            e2, x2 = fo.double_block(sd, 0, cfg, x, enc, temb, rope)
+        td = (time.perf_counter() - t0) / reps
+        h = torch.cat([e2, x2], dim=1)
+        fo.single_block(sd, 0, cfg, h, temb, rope)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fo.single_block(sd, 0, cfg, h, temb, rope)
+        ts = (time.perf_counter() - t0) / reps
+    step_s = full.num_layers * td + full.num_single_layers * ts
+    return dict(value=1.0 / step_s, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"1 double block ({td:.2f} s) + 1 single block ({ts:.2f} s) of the 12B dims at S={S},T={T}, bf16, "
+                       f"x{full.num_layers}/x{full.num_single_layers} -> {step_s:.1f} s/step; embedders and scheduler "
+                       f"(<0.1%) not timed"), step_s
+
+
+def run_reference(args, h2, w2, T, desc):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    vals = []
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_reference_sample(h2, w2, T)
+    last = None
+    for _ in range(max(1, min(args.steps, 3))):
+        last, step_s = cpu_reference_sample(h2, w2, T)
+        vals.append(step_s)
+    step_s = statistics.mean(vals)
+    last["value"] = 1.0 / step_s
+    line = {"metric": METRIC, "value": 1.0 / step_s, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "batch_per_gpu": 1, "note": "reference CPU path on host cores, rank 0 only"},
+            "cpu_baseline": last,
+            "e2e": {"value": 1.0 / step_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, h2, w2, T, desc):
+    from textflux_b200 import B200FluxTransformer, B200FlowMatchEulerScheduler, calculate_shift, synthetic_getter
+    from textflux_b200.engine import FrozenConfig
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = FrozenConfig(patch_size=1, in_channels=384, out_channels=64, num_layers=args.layers or 19,
+                       num_single_layers=args.single_layers or 38, attention_head_dim=128, num_attention_heads=24,
+                       joint_attention_dim=4096, pooled_projection_dim=768, guidance_embeds=True,
+                       axes_dims_rope=(16, 56, 56))
+    S, B = h2 * w2, 1
+    eng = B200FluxTransformer(cfg, synthetic_getter(cfg, 1234, dev), device=dev, gemm_cta_group=args.cta_group,
+                              attn_q_tiles=args.q_tiles)
+    # ---- synthetic inputs: per-sample seeds; prompt embeds + schedule come from rank 0
+    g = torch.Generator(device=dev).manual_seed(1000 + rank)
+    latents0 = torch.randn(B, S, 64, generator=g, device=dev).to(torch.bfloat16)
+    mil = torch.randn(B, S, 64, generator=g, device=dev).to(torch.bfloat16)
+    mask = torch.zeros(B, h2, w2, 256, device=dev, dtype=torch.bfloat16)
+    mask[:, h2 // 2:] = 1  # glyph half 0, scene half fully masked
+    cond = torch.cat([mil, mask.reshape(B, S, 256)], dim=2).contiguous()
+    g0 = torch.Generator(device=dev).manual_seed(999)
+    prompt = torch.randn(1, T, 4096, generator=g0, device=dev).to(torch.bfloat16)
+    pooled = torch.randn(1, 768, generator=g0, device=dev).to(torch.bfloat16)
+    n_sched = 30
+    sch = B200FlowMatchEulerScheduler()
+    mu = calculate_shift(S, sch.config.base_image_seq_len, sch.config.max_image_seq_len, sch.config.base_shift,
+                         sch.config.max_shift)
+    sch.set_timesteps(sigmas=np.linspace(1.0, 1 / n_sched, n_sched), device=dev, mu=mu)
+    sig = sch.sigmas.clone()
+    if world > 1:
+        # the ONE collective of the job: text embeddings + pooled + sigma schedule from rank 0 (NCCL over NVLink)
+        for t in (prompt, pooled, sig):
+            dist.broadcast(t, src=0)
+    sig_cpu = sig.tolist()
+    ts = ((sig[:-1] * 1000)[:, None].expand(-1, B).to(torch.bfloat16) / 1000).contiguous()
+    guidance = torch.full([B], 30.0, device=dev, dtype=torch.float32)
+    ids = torch.zeros(h2, w2, 3)
+    ids[..., 1] += torch.arange(h2)[:, None]
+    ids[..., 2] += torch.arange(w2)[None, :]
+    img_ids = ids.reshape(S, 3).to(dev, torch.bfloat16)
+    txt_ids = torch.zeros(T, 3, device=dev, dtype=torch.bfloat16)
+    prompt_b, pooled_b = prompt.expand(B, -1, -1).contiguous(), pooled.expand(B, -1).contiguous()
+
+    def step(i, lat):
+        k = i % n_sched
+        return eng.step(lat, cond, prompt_b, pooled_b, ts[k], guidance, img_ids, txt_ids, sig_cpu[k], sig_cpu[k + 1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-timed region: inputs resident in HBM
+    lat = latents0
+    for i in range(args.warmup):
+        lat = step(i, lat)
+    barrier()
+    l0 = eng.counter("launches")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        lat = step(args.warmup + i, lat)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.counter("launches") - l0
+    clocks = sampler.stop() if rank == 0 else None
+    finite = bool(torch.isfinite(lat.float()).all())
+
+    # ---- end-to-end through the public API with HOST buffers (pinned): H2D of the step's inputs, D2H of the result
+    host = {k: v.cpu().pin_memory() for k, v in dict(lat=latents0, cond=cond, prompt=prompt_b, pooled=pooled_b, ts=ts,
+                                                      g=guidance, img=img_ids, txt=txt_ids).items()}
+    out_host = torch.empty_like(host["lat"]).pin_memory()
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("lat", "cond", "prompt", "pooled", "g", "img", "txt")) + B * 2
+    d2h = out_host.numel() * out_host.element_size()
+
+    def e2e_step(i):
+        k = i % n_sched
+        d = {n: host[n].to(dev, non_blocking=True) for n in ("lat", "cond", "prompt", "pooled", "g", "img", "txt")}
+        t = host["ts"][k].to(dev, non_blocking=True)
+        new = eng.step(d["lat"], d["cond"], d["prompt"], d["pooled"], t, d["g"], d["img"], d["txt"], sig_cpu[k], sig_cpu[k + 1])
+        out_host.copy_(new, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        host["lat"].copy_(out_host)
+
+    for i in range(min(args.warmup, 2)):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+
+    # ---- per-kernel-family device time, live (eager launches, one CUDA-event pair per kernel)
+    fam = {}
+    if rank == 0:
+        eng.set_option("profile", 1)
+        lat2 = step(0, latents0)
+        torch.cuda.synchronize(dev)
+        for f in ("gemm", "attn", "ln", "gemv", "misc"):
+            fam[f] = {"us": eng.counter(f"prof_us_{f}"), "launches": eng.counter(f"prof_n_{f}")}
+        eng.set_option("profile", 0)
+        del lat2
+
+    if world > 1:
+        tmax = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = tmax.tolist()
+        e2e_s = e2e_ms / 1e3
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_steps = args.steps * B * world
+    value = total_steps / (ms / 1e3)
+    pk = peaks()
+    # algorithmic FLOPs per sample-step (equals FlopCounterMode over the reference model)
+    D, N, L = 3072, S + T, cfg.num_layers + cfg.num_single_layers
+    flops = (L * (24 * N * D * D + 4 * N * N * D) + 2 * S * 384 * D + 2 * T * 4096 * D + 2 * S * D * 64
+             + cfg.num_layers * 2 * (2 * D * 6 * D) + cfg.num_single_layers * (2 * D * 3 * D) + 2 * D * 2 * D
+             + 3 * (2 * 256 * D + 2 * D * D) - 2 * 256 * D + 2 * 768 * D)
+    achieved = flops * B * (args.steps / (ms / 1e3)) / 1e12  # per GPU
+    roof = {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
+            "frac": achieved / pk["sustained"], "frac_of_burst": achieved / pk["burst"], "traffic": None,
+            "launch": "one sampling step (one CUDA-graph launch: every kernel of forward + fused Euler)",
+            "flops_per_launch": flops * B, "peak_source": pk["source"] + ", sustained bf16 figure (timed inside a long step)",
+            "kernel_families_us": fam}
+    if fam.get("gemm", {}).get("us"):
+        gemm_flops = flops - L * 4 * N * N * D
+        roof["gemm_kernel"] = {"achieved": gemm_flops / (fam["gemm"]["us"] * 1e-6) / 1e12, "unit": "TFLOP/s",
+                               "launches": fam["gemm"]["launches"],
+                               "note": "tcgen05 GEMM family alone, eager launches timed with CUDA events"}
+        if fam.get("attn", {}).get("us"):
+            roof["attention_kernel"] = {"achieved": L * 4 * N * N * D / (fam["attn"]["us"] * 1e-6) / 1e12, "unit": "TFLOP/s",
+                                        "launches": fam["attn"]["launches"]}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu, _ = cpu_reference_sample(h2, w2, T)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic (random-init 12B weights, seeded latents/cond/prompt embeds)",
+            "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "image_tokens": S, "text_tokens": T,
+                       "layers": [cfg.num_layers, cfg.num_single_layers], "parallelism": f"replica x{world}",
+                       "l2": "23.8 GB of weights stream through the 126 MB L2 every step (inputs larger than L2)",
+                       "gemm_cta_group": args.cta_group, "attn_q_tiles": args.q_tiles},
+            "clocks": clocks, "gpu_launches": launches, "finite": finite,
+            "e2e": {"value": total_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "roofline": roof, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cta-group", type=int, default=2)
+    ap.add_argument("--q-tiles", type=int, default=2)
+    ap.add_argument("--layers", type=int, default=0, help="debug: override the 19 double blocks (invalidates the number)")
+    ap.add_argument("--single-layers", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    h2, w2, T, desc = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, h2, w2, T, desc)
+    else:
+        run_ours(args, h2, w2, T, desc)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,9 +49,11 @@ int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
 void tfx_destroy(tfx_handle h);
 /* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
 const char* tfx_last_error(tfx_handle h);
-/* "gemm_cta_group" (1|2), "attn_q_tiles" (1|2), "use_graph" (0|1) */
+/* "gemm_cta_group" (1|2), "attn_q_tiles" (1|2), "use_graph" (0|1), "profile" (0|1: eager launches, one CUDA-event
+ * pair per kernel, summed per family; resets the sums) */
 int tfx_set_option(tfx_handle h, const char* key, int64_t value);
-/* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step */
+/* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step;
+ * "prof_us_<fam>" / "prof_n_<fam>" with fam in gemm|attn|ln|gemv|misc: device microseconds / launches in profile mode */
 int tfx_get_counter(tfx_handle h, const char* key, int64_t* value);
 
 /* ---- weights (replaces load_state_dict on the reference module; names listed in INTEGRATION.md) -------------- */

@@ -116,11 +116,43 @@ int num_sms(int device) {
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
+// Optional per-launch device timing (eager mode only): one event pair per launch, summed per kernel family.
+enum KernelFamily : int { KF_GEMM = 0, KF_ATTN = 1, KF_LN = 2, KF_GEMV = 3, KF_MISC = 4, KF_COUNT = 5 };
+struct Profiler {
+  struct Rec { int fam; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  void begin(int fam, cudaStream_t s) {
+    Rec r; r.fam = fam;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t s) { cudaEventRecord(recs.back().b, s); }
+  // returns microseconds and launch counts per family; destroys the events
+  void collect(double (&us)[KF_COUNT], long long (&n)[KF_COUNT]) {
+    for (int i = 0; i < KF_COUNT; ++i) { us[i] = 0; n[i] = 0; }
+    for (auto& r : recs) {
+      cudaEventSynchronize(r.b);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, r.a, r.b);
+      us[r.fam] += ms * 1000.0; n[r.fam] += 1;
+      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    recs.clear();
+  }
+};
+
 struct LaunchCtx {
   cudaStream_t stream;
   int device;
   long long* counter;
   std::string* err_;
+  Profiler* prof = nullptr;
+};
+struct ProfScope {
+  const LaunchCtx& c;
+  ProfScope(const LaunchCtx& c_, int fam) : c(c_) { if (c.prof) c.prof->begin(fam, c.stream); }
+  ~ProfScope() { if (c.prof) c.prof->end(c.stream); }
 };
 
 void configure_kernels(std::string* err_) {
@@ -141,6 +173,7 @@ void launch_gemm(const LaunchCtx& c, int cta_group, const CUtensorMap& a0, const
   std::string* err_ = c.err_;
   REQUIRE(p.K % kGemmBlockK == 0 && p.K > 0, TFX_ERR_INVALID, "GEMM K=%d must be a positive multiple of %d", p.K, kGemmBlockK);
   REQUIRE(p.n_split == p.N || p.n_split % kGemmBlockN == 0, TFX_ERR_INVALID, "n_split %d not tile aligned", p.n_split);
+  ProfScope ps(c, KF_GEMM);
   const int tile_m = 128 * cta_group;
   long long tiles = 0;
   for (int g = 0; g < p.num_groups; ++g) tiles += (p.g[g].M + tile_m - 1) / tile_m;
@@ -176,6 +209,7 @@ void launch_attention(const LaunchCtx& c, int head_dim, int q_tiles, const CUten
   std::string* err_ = c.err_;
   REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
   REQUIRE(q_tiles == 1 || q_tiles == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
+  ProfScope ps(c, KF_ATTN);
   dim3 grid((p.N + 128 * q_tiles - 1) / (128 * q_tiles), p.H, p.B);
   if (head_dim == 128 && q_tiles == 2)
     attention_tcgen05_kernel<128, 2><<<grid, AttnCfg<128, 2>::kThreads, AttnCfg<128, 2>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
@@ -194,6 +228,7 @@ void launch_ln_modulate(const LaunchCtx& c, const LnModParams& p) {
   REQUIRE(p.D % 256 == 0, TFX_ERR_INVALID, "LayerNorm width %d must be a multiple of 256", p.D);
   const int rows = p.rows - p.row_begin;
   if (rows <= 0) return;
+  ProfScope ps(c, KF_LN);
   const int blocks = (rows + 7) / 8;
   switch (p.D / 256) {
     case 1: ln_modulate_kernel<1><<<blocks, 256, 0, c.stream>>>(p); break;
@@ -214,6 +249,7 @@ void launch_gemv(const LaunchCtx& c, const bf16* x, int B, int K, const bf16* W,
   REQUIRE(B >= 1 && B <= kGemvMaxB, TFX_ERR_INVALID, "batch %d unsupported (1..%d)", B, kGemvMaxB);
   const size_t smem = (size_t)B * K * 2;
   REQUIRE(smem <= 48 * 1024, TFX_ERR_INVALID, "GEMV input %zu bytes exceeds 48 KiB", smem);
+  ProfScope ps(c, KF_GEMV);
   long long blocks = (N + 7) / 8;
   const long long cap = (long long)num_sms(c.device) * 8;
   if (blocks > cap) blocks = cap;
@@ -240,6 +276,10 @@ struct tfx_model {
   int gemm_cta_group = 1;
   int attn_q_tiles = 2;
   int use_graph = 1;
+  int profile = 0;
+  Profiler prof;
+  double prof_us[KF_COUNT] = {0, 0, 0, 0, 0};
+  long long prof_n[KF_COUNT] = {0, 0, 0, 0, 0};
   bool finalized = false;
   std::map<std::string, Weight> w;
 
@@ -539,6 +579,15 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
 void tfx_model::run(bool fused_euler, bool want_noise_pred) {
   LaunchCtx c{stream, device, &launches, err_};
   cudaGraphExec_t& exec = fused_euler ? graph_step : graph_fwd;
+  if (profile) {
+    c.prof = &prof;
+    enqueue_forward(c, fused_euler, want_noise_pred);
+    double us[KF_COUNT];
+    long long n[KF_COUNT];
+    prof.collect(us, n);
+    for (int i = 0; i < KF_COUNT; ++i) { prof_us[i] += us[i]; prof_n[i] += n[i]; }
+    return;
+  }
   if (!use_graph) {
     enqueue_forward(c, fused_euler, want_noise_pred);
     return;
@@ -640,6 +689,9 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
     h->attn_q_tiles = (int)value;
   } else if (k == "use_graph") {
     h->use_graph = value != 0;
+  } else if (k == "profile") {
+    h->profile = value != 0;
+    for (int i = 0; i < KF_COUNT; ++i) { h->prof_us[i] = 0; h->prof_n[i] = 0; }
   } else {
     REQUIRE(false, TFX_ERR_INVALID, "unknown option '%s'", key);
   }
@@ -654,6 +706,15 @@ int tfx_get_counter(tfx_handle h, const char* key, int64_t* value) {
   std::string k(key);
   if (k == "launches") *value = h->launches;
   else if (k == "graph_nodes") *value = h->graph_nodes;
+  else if (k.compare(0, 8, "prof_us_") == 0 || k.compare(0, 7, "prof_n_") == 0) {
+    const bool is_us = k.compare(0, 8, "prof_us_") == 0;
+    const std::string fam = k.substr(is_us ? 8 : 7);
+    static const char* names[KF_COUNT] = {"gemm", "attn", "ln", "gemv", "misc"};
+    int idx = -1;
+    for (int i = 0; i < KF_COUNT; ++i) if (fam == names[i]) idx = i;
+    REQUIRE(idx >= 0, TFX_ERR_INVALID, "unknown kernel family '%s'", fam.c_str());
+    *value = is_us ? (long long)(h->prof_us[idx] + 0.5) : h->prof_n[idx];
+  }
   else REQUIRE(false, TFX_ERR_INVALID, "unknown counter '%s'", key);
   API_END
 }

@@ -1,0 +1,90 @@
+"""Kernel micro-benchmarks through the C ABI (CUDA events, L2-cold via a flush buffer): GEMM shapes of the FLUX blocks
+and joint attention, in TFLOP/s.  Usage: python tools/bench_kernels.py [--json out.json]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from textflux_b200 import _lib  # noqa: E402
+
+
+def timeit(fn, iters=10, flush=None):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--json", default=None)
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    lib = _lib.load()
+    st = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    res = []
+    shapes = [(2560, 9216, 3072, "qkv (double, per stream-pair)"), (2560, 3072, 3072, "out-proj"),
+              (2560, 12288, 3072, "ff up"), (2560, 3072, 12288, "ff down"), (2560, 21504, 3072, "single qkv+mlp"),
+              (2560, 3072, 15360, "single proj_out"), (5120, 21504, 3072, "single qkv+mlp cfg3"),
+              (8192, 8192, 8192, "square 8192")]
+    if args.quick:
+        shapes = shapes[:4]
+    for M, N, K, name in shapes:
+        A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+        W = (torch.randn(N, K, device="cuda") * 0.02).to(torch.bfloat16)
+        b = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        row = {"kernel": "gemm", "name": name, "M": M, "N": N, "K": K}
+        for cg in (1, 2):
+            def f():
+                _lib.check(lib.tfx_op_linear(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), out.data_ptr(), N, M, N, K, 0, None, None, cg, st))
+            ms = timeit(f, flush=flush)
+            row[f"cg{cg}_ms"] = ms
+            row[f"cg{cg}_tflops"] = 2.0 * M * N * K / ms / 1e9
+        ms = timeit(lambda: torch.nn.functional.linear(A, W, b), flush=flush)
+        row["cublas_ms"] = ms
+        row["cublas_tflops"] = 2.0 * M * N * K / ms / 1e9
+        print(row, flush=True)
+        res.append(row)
+        del A, W, out
+    for (T, S) in [(512, 2048), (512, 4608), (512, 8192)]:
+        H, dh, N = 24, 128, T + S
+        q = torch.randn(1, H, N, dh, device="cuda").to(torch.bfloat16)
+        k = torch.randn(1, H, N, dh, device="cuda").to(torch.bfloat16)
+        v = torch.randn(1, H, N, dh, device="cuda").to(torch.bfloat16)
+        out = torch.empty(N, H * dh, device="cuda", dtype=torch.bfloat16)
+        row = {"kernel": "attention", "N": N, "H": H, "dh": dh}
+        fl = 4.0 * N * N * H * dh
+        for qt in (1, 2):
+            def f():
+                _lib.check(lib.tfx_op_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), H * dh, 1, H, T, S, dh, qt, st))
+            ms = timeit(f, flush=flush)
+            row[f"qt{qt}_ms"] = ms
+            row[f"qt{qt}_tflops"] = fl / ms / 1e9
+        ms = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), flush=flush)
+        row["sdpa_ms"] = ms
+        row["sdpa_tflops"] = fl / ms / 1e9
+        print(row, flush=True)
+        res.append(row)
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump(res, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
