@@ -119,6 +119,23 @@ def test_linear_gelu_and_gate_res(lib, cta_group):
     assert _rel(out, ref) < 4e-3
 
 
+@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
+@pytest.mark.parametrize("bn", [224, 192])
+def test_linear_narrow_tiles(lib, monkeypatch, bn, cta_group):
+    """224- and 192-wide tiles (picked by the host against wave quantisation) give the same results."""
+    monkeypatch.setenv("TFX_OP_LINEAR_BLOCK_N", str(bn))
+    for (M, N, K) in [(2560, 3072, 3072), (300, 320, 192), (512, 448, 128)]:
+        g = torch.Generator(device="cuda").manual_seed(M + N + K + bn)
+        A = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+        W = (torch.randn(N, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+        b = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+        gate = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+        res = torch.randn(M, N, generator=g, device="cuda").to(torch.bfloat16)
+        lin = (A.float() @ W.float().T + b.float())
+        assert _rel(_linear(lib, A, W, b, 0, cta_group), lin) < 4e-3
+        assert _rel(_linear(lib, A, W, b, 2, cta_group, gate=gate, res=res), res + gate * lin.to(torch.bfloat16)) < 4e-3
+
+
 def test_linear_strided_a(lib):
     """A operand read out of a wider buffer (the [attn | mlp] concat tile): lda > K."""
     M, N, K, LD = 256, 256, 128, 640
@@ -183,7 +200,7 @@ def test_ln_modulate(lib, rows, D, per):
     ref = torch.nn.functional.layer_norm(xb, (D,), None, None, 1e-6) * (1 + scale[:, None]) + shift[:, None]
     ref32 = torch.nn.functional.layer_norm(xb.float(), (D,), None, None, 1e-6) * (1 + scale.float()[:, None]) + shift.float()[:, None]
     assert _rel(y.view(Bn, per, D), ref32) <= _rel(ref, ref32) * 1.5 + 1e-4
-    assert _rel(y.view(Bn, per, D), ref) < 5e-3
+    assert _rel(y.view(Bn, per, D), ref) < 6e-3
 
 
 @pytest.mark.parametrize("B,K,N,flags", [(1, 256, 3072, 2), (2, 3072, 18432, 1), (3, 32, 256, 2), (8, 3072, 1000, 0), (1, 3072, 4097, 1)])

@@ -177,52 +177,61 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     const uint32_t t_o = t_lane + uint32_t(Cfg::kOCol + q * 128);
     const float c = p.scale_log2;
     float m = -INFINITY, l = 0.f;
+    const float kRescaleThreshold = 8.0f;  // log2 units: keep a stale row max until it is off by more than 2^8
     for (int j = 0; j < n_kv; ++j) {
-      const int valid = min(128, p.N - j * 128);  // columns of this tile that are real keys
+      const int valid = p.N - j * 128;  // >= 128 on every tile but possibly the last
       mbar_wait(&s_full[q], j & 1);
       tc_fence_after();
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int cch = 0; cch < 4; ++cch) {
-        uint32_t v[32];
-        tmem_ld32(t_s + cch * 32, v);
-        tmem_ld_wait();
-        if (valid >= (cch + 1) * 32) {
+      // the whole 128-column score row of this thread in registers: one TMEM pass
+      uint32_t sr[4][32];
+      tmem_ld32(t_s + 0, sr[0]);
+      tmem_ld32(t_s + 32, sr[1]);
+      tmem_ld32(t_s + 64, sr[2]);
+      tmem_ld32(t_s + 96, sr[3]);
+      tmem_ld_wait();
+      if (valid < 128) {  // ragged last tile: keys past N score -inf -> probability 0
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
+        for (int cch = 0; cch < 4; ++cch)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) if (cch * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
+          for (int i = 0; i < 32; ++i)
+            if (cch * 32 + i >= valid) sr[cch][i] = 0xff800000u;
       }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = ex2((m - m_new) * c);  // 0 on the first tile (m = -inf)
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+        mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
+        mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // lazy rescaling: the reference point m only moves when the true max ran away from it
+      const bool need = (mx - m) * c > kRescaleThreshold;  // true on the first tile (m = -inf)
+      const float m_new = need ? mx : m;
+      const float alpha = need ? ex2((m - m_new) * c) : 1.0f;
       const float mc = m_new * c;
-      float rowsum = 0.f;
-#pragma unroll 1
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[2][32];
+#pragma unroll
       for (int cch = 0; cch < 4; ++cch) {
-        uint32_t v[32];
-        uint32_t pk[16];
-        tmem_ld32(t_s + cch * 32, v);
-        tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2(fmaf(__uint_as_float(v[i]), c, -mc));
-          float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), c, -mc));
-          if (cch * 32 + i >= valid) p0 = 0.f;
-          if (cch * 32 + i + 1 >= valid) p1 = 0.f;
-          rowsum += p0 + p1;
-          pk[i / 2] = pack_bf16(p0, p1);
+          const float p0 = ex2(fmaf(__uint_as_float(sr[cch][i]), c, -mc));
+          const float p1 = ex2(fmaf(__uint_as_float(sr[cch][i + 1]), c, -mc));
+          sum0 += p0;
+          sum1 += p1;
+          pk[cch >> 1][(cch & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
         }
-        tmem_st16(t_s + cch * 16, pk);  // P (bf16 pairs) over S columns already consumed
       }
-      l = l * alpha + rowsum;
+      tmem_st32(t_s + 0, pk[0]);  // P (bf16 pairs) over the S columns just consumed
+      tmem_st32(t_s + 32, pk[1]);
+      l = l * alpha + (sum0 + sum1);
       m = m_new;
       tmem_st_wait();
       if (j > 0) {
         mbar_wait(&pv_done[q], (j - 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+        if (__any_sync(0xffffffffu, need)) {
 #pragma unroll 1
           for (int cch = 0; cch < kHeadDim / 32; ++cch) {
             uint32_t v[32];

@@ -60,14 +60,16 @@ struct GemmParams {
   const float* dt_ptr;  // EULER: device scalar float(bf16(sigma_next - sigma))
 };
 
-constexpr int kGemmBlockN = 256;
+constexpr int kGemmBlockN = 256;  // default tile width; 224 / 192 are instantiated to cut wave quantisation
 constexpr int kGemmBlockK = 64;
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue (2 per TMEM lane quadrant)
+constexpr int kGemmEpiWarps = 8;
 
-template <int kCtaGroup>
+template <int kCtaGroup, int kBN = kGemmBlockN>
 struct GemmCfg {
+  static_assert(kBN % 32 == 0 && kBN <= 256, "tile width must be a multiple of 32 (epilogue chunk) and fit one UMMA");
   static constexpr int kTileM = 128 * kCtaGroup;
-  static constexpr int kBRows = kGemmBlockN / kCtaGroup;  // rows of W each CTA loads
+  static constexpr int kBRows = kBN / kCtaGroup;  // rows of W each CTA loads
   static constexpr int kABytes = 128 * kGemmBlockK * 2;
   static constexpr int kBBytes = kBRows * kGemmBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -114,13 +116,14 @@ __device__ __forceinline__ void linear_out(const uint32_t (&v)[32], const __nv_b
   for (int i = 0; i < 32; ++i) x[i] = bf16_round(__uint_as_float(v[i]) + b[i]);
 }
 
-template <int kCtaGroup>
+template <int kCtaGroup, int kBN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                     const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<kCtaGroup>;
+  using Cfg = GemmCfg<kCtaGroup, kBN>;
   constexpr int kStages = Cfg::kStages;
+  constexpr int kChunks = kBN / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -151,7 +154,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4 * kCtaGroup);
+      mbar_init(&tmem_empty_bar[i], kGemmEpiWarps * kCtaGroup);
     }
     fence_mbar_init();
   }
@@ -168,7 +171,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const int mt0 = (p.g[0].M + Cfg::kTileM - 1) / Cfg::kTileM;
   const int mt1 = (p.num_groups > 1) ? (p.g[1].M + Cfg::kTileM - 1) / Cfg::kTileM : 0;
   const int MT = mt0 + mt1;
-  const int NT = (p.N + kGemmBlockN - 1) / kGemmBlockN;
+  const int NT = (p.N + kBN - 1) / kBN;
   const int num_tiles = MT * NT;
   const int KB = p.K / kGemmBlockK;
   const int first_tile = blockIdx.x / kCtaGroup;
@@ -182,7 +185,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const int mi = t % MT, ni = t / MT;
       const int grp = (mi < mt0) ? 0 : 1;
       const int m0 = (grp ? mi - mt0 : mi) * Cfg::kTileM + int(cta_rank) * 128;
-      const int n0 = ni * kGemmBlockN + int(cta_rank) * Cfg::kBRows;
+      const int n0 = ni * kBN + int(cta_rank) * Cfg::kBRows;
       const CUtensorMap* tA = grp ? &tmA1 : &tmA0;
       const CUtensorMap* tB = grp ? &tmB1 : &tmB0;
       for (int kb = 0; kb < KB; ++kb) {
@@ -204,7 +207,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (is_leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(Cfg::kTileM, kGemmBlockN, 0, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(Cfg::kTileM, kBN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -213,7 +216,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         if constexpr (kCtaGroup == 2) mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
         else mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + uint32_t(acc * kGemmBlockN);
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * 256);
         for (int kb = 0; kb < KB; ++kb) {
           if constexpr (kCtaGroup == 2) mbar_wait_cluster(&full_bar[stage], phase);
           else mbar_wait(&full_bar[stage], phase);
@@ -238,7 +241,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     }
   } else if (warp >= 4) {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;  // which half of the tile's 256 columns this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = first_tile; t < num_tiles; t += tile_step) {
@@ -247,7 +251,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const GemmGroup& G = p.g[grp];
       const int m_local = (grp ? mi - mt0 : mi) * Cfg::kTileM + int(cta_rank) * 128 + quad * 32 + lane;
       const bool row_ok = m_local < G.M;
-      const int n_tile0 = ni * kGemmBlockN;
+      const int n_tile0 = ni * kBN;
       const int mode = (n_tile0 < p.n_split) ? p.mode0 : p.mode1;
       const int bidx = m_local / G.rows_per_sample;
       const int pos = G.pos_offset + (m_local - bidx * G.rows_per_sample);
@@ -255,17 +259,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       if constexpr (kCtaGroup == 2) mbar_wait_cluster(&tmem_full_bar[acc], acc_phase);
       else mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * kGemmBlockN);
+      const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 256);
 
       if (mode == EPI_QKV) {
         const int sect = n_tile0 / p.D;  // 0 q, 1 k, 2 v
         const int dh = p.head_dim;
         const int head0 = (n_tile0 - sect * p.D) / dh;
-        const int heads_in_tile = kGemmBlockN / dh;
+        const int heads_in_tile = kBN / dh;  // QKV launches use kBN = 256 (host-enforced): 2 or 4 heads per tile
         const int chunks_per_head = dh / 32;
         __nv_bfloat16* dst_base = (sect == 0) ? p.q : (sect == 1) ? p.k : p.v;
         const __nv_bfloat16* rmsw = (sect == 0) ? G.rms_q : G.rms_k;
-        for (int hh = 0; hh < heads_in_tile; ++hh) {
+        for (int hh = half * (heads_in_tile / 2); hh < (half + 1) * (heads_in_tile / 2); ++hh) {
           const int head = head0 + hh;
           if (n_tile0 + hh * dh >= p.N) break;
           __nv_bfloat16* dst = dst_base + ((long long)(bidx * p.num_heads + head) * p.n_joint + pos) * dh;
@@ -314,7 +318,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         }
       } else {
         const int n_out0 = (n_tile0 < p.n_split) ? n_tile0 : (n_tile0 - p.n_split + p.col_offset1);
-        for (int c = 0; c < kGemmBlockN / 32; ++c) {
+        for (int c = half * ((kChunks + 1) / 2); c < (half ? kChunks : (kChunks + 1) / 2); ++c) {
           const int n = n_tile0 + c * 32;
           if (n >= p.N) break;  // warp-uniform
           uint32_t v[32];

@@ -254,11 +254,14 @@ __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u 
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
 // tanh-GELU exactly as ATen evaluates it in fp32 opmath: 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715 x^3)))
+// evaluated through the identity 0.5*(1+tanh(u)) = sigmoid(2u) = 1/(1+2^(-2u*log2 e)): one EX2 + one RCP.
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float kBeta = 0.7978845608028654f;  // sqrt(2/pi)
   const float kKappa = 0.044715f;
-  float inner = kBeta * (x + kKappa * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  const float u = kBeta * fmaf(kKappa * x * x, x, x);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(u * -2.8853900817779268f));  // 2^(-2u log2 e) = exp(-2u)
+  return __fdividef(x, 1.0f + e);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -158,8 +159,12 @@ struct ProfScope {
 void configure_kernels(std::string* err_) {
   static bool done = false;
   if (done) return;
-  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 256>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 256>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 224>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 224>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 192>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 192>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 1>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 1>::kSmemBytes));
@@ -168,38 +173,69 @@ void configure_kernels(std::string* err_) {
   done = true;
 }
 
-void launch_gemm(const LaunchCtx& c, int cta_group, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
-                 const CUtensorMap& b1, const GemmParams& p) {
+// Tile width that minimises (waves x width) for an [M, N] output on `units` concurrent tiles (SMs or SM pairs).
+int pick_block_n(long long m_tiles, int N, int units, bool allow_narrow) {
+  int best = 256;
+  long long best_cost = -1;
+  const int cands[3] = {256, 224, 192};
+  for (int i = 0; i < (allow_narrow ? 3 : 1); ++i) {
+    const int bn = cands[i];
+    const long long tiles = m_tiles * ((N + bn - 1) / bn);
+    const long long cost = ((tiles + units - 1) / units) * bn;
+    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+
+template <int kCG, int kBN>
+void launch_gemm_inst(const LaunchCtx& c, long long tiles, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
+                      const CUtensorMap& b1, const GemmParams& p) {
   std::string* err_ = c.err_;
-  REQUIRE(p.K % kGemmBlockK == 0 && p.K > 0, TFX_ERR_INVALID, "GEMM K=%d must be a positive multiple of %d", p.K, kGemmBlockK);
-  REQUIRE(p.n_split == p.N || p.n_split % kGemmBlockN == 0, TFX_ERR_INVALID, "n_split %d not tile aligned", p.n_split);
-  ProfScope ps(c, KF_GEMM);
-  const int tile_m = 128 * cta_group;
-  long long tiles = 0;
-  for (int g = 0; g < p.num_groups; ++g) tiles += (p.g[g].M + tile_m - 1) / tile_m;
-  tiles *= (p.N + kGemmBlockN - 1) / kGemmBlockN;
-  if (tiles == 0) return;
   const int sms = num_sms(c.device);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
   cudaLaunchAttribute attr[1];
   cfg.blockDim = dim3(kGemmThreads);
   cfg.stream = c.stream;
-  if (cta_group == 2) {
-    long long clusters = tiles < sms / 2 ? tiles : sms / 2;
+  cfg.dynamicSmemBytes = GemmCfg<kCG, kBN>::kSmemBytes;
+  if (kCG == 2) {
+    const long long clusters = tiles < sms / 2 ? tiles : sms / 2;
     cfg.gridDim = dim3((unsigned)(clusters * 2));
-    cfg.dynamicSmemBytes = GemmCfg<2>::kSmemBytes;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<2>, a0, a1, b0, b1, p));
   } else {
     cfg.gridDim = dim3((unsigned)(tiles < sms ? tiles : sms));
-    cfg.dynamicSmemBytes = GemmCfg<1>::kSmemBytes;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<1>, a0, a1, b0, b1, p));
+  }
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<kCG, kBN>, a0, a1, b0, b1, p));
+}
+
+// b0/b1 must be descriptors whose box holds block_n / cta_group rows.
+void launch_gemm(const LaunchCtx& c, int cta_group, int block_n, const CUtensorMap& a0, const CUtensorMap& a1,
+                 const CUtensorMap& b0, const CUtensorMap& b1, const GemmParams& p) {
+  std::string* err_ = c.err_;
+  REQUIRE(p.K % kGemmBlockK == 0 && p.K > 0, TFX_ERR_INVALID, "GEMM K=%d must be a positive multiple of %d", p.K, kGemmBlockK);
+  REQUIRE(p.n_split == p.N || p.n_split % block_n == 0, TFX_ERR_INVALID, "n_split %d not tile aligned", p.n_split);
+  const bool qkv = p.mode0 == EPI_QKV || (p.n_split < p.N && p.mode1 == EPI_QKV);
+  REQUIRE(!qkv || block_n == 256, TFX_ERR_INVALID, "QKV epilogue needs 256-wide tiles");
+  ProfScope ps(c, KF_GEMM);
+  const int tile_m = 128 * cta_group;
+  long long tiles = 0;
+  for (int g = 0; g < p.num_groups; ++g) tiles += (p.g[g].M + tile_m - 1) / tile_m;
+  tiles *= (p.N + block_n - 1) / block_n;
+  if (tiles == 0) return;
+  const int key = cta_group * 1000 + block_n;
+  switch (key) {
+    case 1256: launch_gemm_inst<1, 256>(c, tiles, a0, a1, b0, b1, p); break;
+    case 2256: launch_gemm_inst<2, 256>(c, tiles, a0, a1, b0, b1, p); break;
+    case 1224: launch_gemm_inst<1, 224>(c, tiles, a0, a1, b0, b1, p); break;
+    case 2224: launch_gemm_inst<2, 224>(c, tiles, a0, a1, b0, b1, p); break;
+    case 1192: launch_gemm_inst<1, 192>(c, tiles, a0, a1, b0, b1, p); break;
+    case 2192: launch_gemm_inst<2, 192>(c, tiles, a0, a1, b0, b1, p); break;
+    default: REQUIRE(false, TFX_ERR_INVALID, "no GEMM instance for cta_group %d block_n %d", cta_group, block_n);
   }
   ++*c.counter;
 }
@@ -229,14 +265,14 @@ void launch_ln_modulate(const LaunchCtx& c, const LnModParams& p) {
   const int rows = p.rows - p.row_begin;
   if (rows <= 0) return;
   ProfScope ps(c, KF_LN);
-  const int blocks = (rows + 7) / 8;
+  const int blocks = (rows + 3) / 4;
   switch (p.D / 256) {
-    case 1: ln_modulate_kernel<1><<<blocks, 256, 0, c.stream>>>(p); break;
-    case 2: ln_modulate_kernel<2><<<blocks, 256, 0, c.stream>>>(p); break;
-    case 4: ln_modulate_kernel<4><<<blocks, 256, 0, c.stream>>>(p); break;
-    case 8: ln_modulate_kernel<8><<<blocks, 256, 0, c.stream>>>(p); break;
-    case 12: ln_modulate_kernel<12><<<blocks, 256, 0, c.stream>>>(p); break;
-    case 16: ln_modulate_kernel<16><<<blocks, 256, 0, c.stream>>>(p); break;
+    case 1: ln_modulate_kernel<1><<<blocks, 128, 0, c.stream>>>(p); break;
+    case 2: ln_modulate_kernel<2><<<blocks, 128, 0, c.stream>>>(p); break;
+    case 4: ln_modulate_kernel<4><<<blocks, 128, 0, c.stream>>>(p); break;
+    case 8: ln_modulate_kernel<8><<<blocks, 128, 0, c.stream>>>(p); break;
+    case 12: ln_modulate_kernel<12><<<blocks, 128, 0, c.stream>>>(p); break;
+    case 16: ln_modulate_kernel<16><<<blocks, 128, 0, c.stream>>>(p); break;
     default: REQUIRE(false, TFX_ERR_INVALID, "LayerNorm width %d unsupported", p.D);
   }
   CUDA_TRY(cudaGetLastError());
@@ -298,7 +334,7 @@ struct tfx_model {
   // activation-side TMA descriptors, [0] text rows, [1] image rows
   CUtensorMap mA_nbuf[2], mA_attn[2], mA_mlp[2], mA_cat[2], mA_x, mA_enc, mA_final;
   CUtensorMap mQ, mK, mV;
-  std::map<std::string, CUtensorMap> mB[3];  // [cta_group] weight-side descriptors by weight name
+  std::map<std::string, CUtensorMap> mB;  // weight-side descriptors, keyed "<weight>#<cta_group>#<block_n>"
 
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
@@ -309,10 +345,21 @@ struct tfx_model {
     REQUIRE(it != w.end(), TFX_ERR_MISSING, "weight '%s' was never set", name.c_str());
     return it->second;
   }
-  const CUtensorMap& WB(const std::string& name) {
-    auto it = mB[gemm_cta_group].find(name);
-    REQUIRE(it != mB[gemm_cta_group].end(), TFX_ERR_STATE, "no TMA descriptor for '%s'", name.c_str());
+  const CUtensorMap& WB(const std::string& name, int block_n = kGemmBlockN) {
+    const std::string key = name + "#" + std::to_string(gemm_cta_group) + "#" + std::to_string(block_n);
+    auto it = mB.find(key);
+    if (it == mB.end()) {
+      const Weight& t = W(name);
+      REQUIRE(t.cols % kGemmBlockK == 0, TFX_ERR_INVALID, "weight '%s' has K=%lld, not a multiple of %d", name.c_str(), t.cols, kGemmBlockK);
+      it = mB.emplace(key, make_map_2d(err_, t.ptr, t.rows, t.cols, t.cols, block_n / gemm_cta_group)).first;
+    }
     return it->second;
+  }
+  // tile width for a two-stream (text rows + image rows) GEMM of width Nn
+  int block_n_for(int Nn) const {
+    const int tile_m = 128 * gemm_cta_group;
+    const long long mt = ((long long)B * T + tile_m - 1) / tile_m + ((long long)B * S + tile_m - 1) / tile_m;
+    return pick_block_n(mt, Nn, num_sms(device) / gemm_cta_group, true);
   }
   void free_workspace() {
     for (void* p : allocs) cudaFree(p);
@@ -339,19 +386,7 @@ struct tfx_model {
   void run(bool fused_euler, bool want_noise_pred);
 };
 
-void tfx_model::build_weight_maps() {
-  for (int cg = 1; cg <= 2; ++cg) {
-    mB[cg].clear();
-    for (auto& kv : w) {
-      const std::string& name = kv.first;
-      if (name.size() < 2 || name.compare(name.size() - 2, 2, ".w") != 0) continue;
-      if (name.compare(0, 4, "mod.") == 0 || name.find("_embed.") != std::string::npos) continue;  // GEMV weights
-      const Weight& t = kv.second;
-      REQUIRE(t.cols % kGemmBlockK == 0, TFX_ERR_INVALID, "weight '%s' has K=%lld, not a multiple of %d", name.c_str(), t.cols, kGemmBlockK);
-      mB[cg][name] = make_map_2d(err_, t.ptr, t.rows, t.cols, t.cols, kGemmBlockN / cg);
-    }
-  }
-}
+void tfx_model::build_weight_maps() { mB.clear(); }
 
 void tfx_model::prepare(int B_, int S_, int T_) {
   REQUIRE(finalized, TFX_ERR_STATE, "tfx_prepare before tfx_finalize_weights");
@@ -455,12 +490,12 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     GemmParams p = base_params(D, cfg.joint_attention_dim);
     p.num_groups = 1;
     p.g[0].bias = W("context_embedder.b").ptr; p.g[0].out = hidden; p.g[0].ldo = D;
-    launch_gemm(c, gemm_cta_group, mA_enc, mA_enc, WB("context_embedder.w"), WB("context_embedder.w"), p);
+    launch_gemm(c, gemm_cta_group, 256, mA_enc, mA_enc, WB("context_embedder.w"), WB("context_embedder.w"), p);
     GemmParams px = base_params(D, cfg.in_channels);
     px.num_groups = 1;
     px.g[0] = px.g[1];
     px.g[0].bias = W("x_embedder.b").ptr; px.g[0].out = hidden + rt * D; px.g[0].ldo = D;
-    launch_gemm(c, gemm_cta_group, mA_x, mA_x, WB("x_embedder.w"), WB("x_embedder.w"), px);
+    launch_gemm(c, gemm_cta_group, 256, mA_x, mA_x, WB("x_embedder.w"), WB("x_embedder.w"), px);
   }
   AttnParams ap;
   ap.B = B; ap.H = H; ap.N = N; ap.T = T; ap.S = S;
@@ -471,6 +506,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
   lp.x = hidden; lp.y = nbuf; lp.rows = (int)(rt + ri); lp.D = D; lp.row_begin = 0; lp.rows0 = (int)rt;
   lp.rows_per0 = T; lp.rows_per1 = S; lp.mod = mod; lp.mod_stride = mod_rows; lp.eps = 1e-6f;
 
+  const int bn_d = block_n_for(D), bn_4d = block_n_for(4 * D);  // tile widths chosen against wave quantisation
   bf16* hid_g[2] = {hidden, hidden + rt * D};
   bf16* cat_g[2] = {cat, cat + rt * 5 * D};
 
@@ -488,7 +524,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].rms_q = W(name("d%d.rms_q", i, sfx[g])).ptr;
         p.g[g].rms_k = W(name("d%d.rms_k", i, sfx[g])).ptr;
       }
-      launch_gemm(c, gemm_cta_group, mA_nbuf[0], mA_nbuf[1], WB(name("d%d.qkv_c", i, ".w")), WB(name("d%d.qkv_x", i, ".w")), p);
+      launch_gemm(c, gemm_cta_group, 256, mA_nbuf[0], mA_nbuf[1], WB(name("d%d.qkv_c", i, ".w")), WB(name("d%d.qkv_x", i, ".w")), p);
     }
     launch_attention(c, dh, attn_q_tiles, mQ, mK, mV, ap);
     {
@@ -499,7 +535,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].out = hid_g[g]; p.g[g].ldo = D; p.g[g].res = hid_g[g]; p.g[g].ldr = D;
         p.g[g].gate = mod + mod_double(i, g == 0, 2); p.g[g].gate_stride = mod_rows;
       }
-      launch_gemm(c, gemm_cta_group, mA_attn[0], mA_attn[1], WB(name("d%d.out_c", i, ".w")), WB(name("d%d.out_x", i, ".w")), p);
+      launch_gemm(c, gemm_cta_group, bn_d, mA_attn[0], mA_attn[1], WB(name("d%d.out_c", i, ".w"), bn_d), WB(name("d%d.out_x", i, ".w"), bn_d), p);
     }
     lp.shift0 = mod_double(i, 1, 3); lp.scale0 = mod_double(i, 1, 4);
     lp.shift1 = mod_double(i, 0, 3); lp.scale1 = mod_double(i, 0, 4);
@@ -511,7 +547,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].bias = W(name("d%d.ff1", i, sfx[g]) + ".b").ptr;
         p.g[g].out = cat_g[g] + D; p.g[g].ldo = 5LL * D;
       }
-      launch_gemm(c, gemm_cta_group, mA_nbuf[0], mA_nbuf[1], WB(name("d%d.ff1_c", i, ".w")), WB(name("d%d.ff1_x", i, ".w")), p);
+      launch_gemm(c, gemm_cta_group, bn_4d, mA_nbuf[0], mA_nbuf[1], WB(name("d%d.ff1_c", i, ".w"), bn_4d), WB(name("d%d.ff1_x", i, ".w"), bn_4d), p);
     }
     {
       GemmParams p = base_params(D, 4 * D);
@@ -521,7 +557,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].out = hid_g[g]; p.g[g].ldo = D; p.g[g].res = hid_g[g]; p.g[g].ldr = D;
         p.g[g].gate = mod + mod_double(i, g == 0, 5); p.g[g].gate_stride = mod_rows;
       }
-      launch_gemm(c, gemm_cta_group, mA_mlp[0], mA_mlp[1], WB(name("d%d.ff2_c", i, ".w")), WB(name("d%d.ff2_x", i, ".w")), p);
+      launch_gemm(c, gemm_cta_group, bn_d, mA_mlp[0], mA_mlp[1], WB(name("d%d.ff2_c", i, ".w"), bn_d), WB(name("d%d.ff2_x", i, ".w"), bn_d), p);
     }
   }
   // --- 38 x FluxSingleTransformerBlock (transformer_flux.py:715-739) on the joint [text;image] rows (the cat of
@@ -540,7 +576,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].out = cat_g[g]; p.g[g].ldo = 5LL * D;
       }
       const CUtensorMap& wb = WB(name("s%d.qkvmlp", j, ".w"));
-      launch_gemm(c, gemm_cta_group, mA_nbuf[0], mA_nbuf[1], wb, wb, p);
+      launch_gemm(c, gemm_cta_group, 256, mA_nbuf[0], mA_nbuf[1], wb, wb, p);
     }
     launch_attention(c, dh, attn_q_tiles, mQ, mK, mV, ap);
     {
@@ -551,8 +587,8 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].out = hid_g[g]; p.g[g].ldo = D; p.g[g].res = hid_g[g]; p.g[g].ldr = D;
         p.g[g].gate = mod + mod_single(j, 2); p.g[g].gate_stride = mod_rows;
       }
-      const CUtensorMap& wb = WB(name("s%d.out", j, ".w"));
-      launch_gemm(c, gemm_cta_group, mA_cat[0], mA_cat[1], wb, wb, p);
+      const CUtensorMap& wb = WB(name("s%d.out", j, ".w"), bn_d);
+      launch_gemm(c, gemm_cta_group, bn_d, mA_cat[0], mA_cat[1], wb, wb, p);
     }
   }
   // --- norm_out (AdaLayerNormContinuous: chunk order scale, shift) + proj_out on the image rows (:1200-1203)
@@ -572,7 +608,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     } else {
       p.g[0].out = out_buf; p.g[0].ldo = C;
     }
-    launch_gemm(c, gemm_cta_group, mA_final, mA_final, WB("proj_out.w"), WB("proj_out.w"), p);
+    launch_gemm(c, gemm_cta_group, 256, mA_final, mA_final, WB("proj_out.w"), WB("proj_out.w"), p);
   }
 }
 
@@ -872,8 +908,11 @@ int tfx_op_linear(const void* A, int64_t lda, const void* Wt, const void* bias, 
     CUDA_TRY(cudaGetDevice(&dev));
     configure_kernels(err_);
     if (M == 0) return TFX_OK;
+    const char* force = getenv("TFX_OP_LINEAR_BLOCK_N");  // tests pin a tile width through this
+    const int bn = force ? atoi(force) : pick_block_n((M + 128 * cta_group - 1) / (128 * cta_group), N, num_sms(dev) / cta_group, true);
+    REQUIRE(bn == 256 || bn == 224 || bn == 192, TFX_ERR_INVALID, "TFX_OP_LINEAR_BLOCK_N must be 256, 224 or 192");
     CUtensorMap ma = make_map_2d(err_, A, M, K, lda, 128);
-    CUtensorMap mb = make_map_2d(err_, Wt, N, K, K, kGemmBlockN / cta_group);
+    CUtensorMap mb = make_map_2d(err_, Wt, N, K, K, bn / cta_group);
     GemmParams p;
     memset(&p, 0, sizeof p);
     p.N = N; p.K = K; p.num_groups = 1; p.n_split = N; p.mode0 = mode; p.mode1 = mode;
@@ -882,7 +921,7 @@ int tfx_op_linear(const void* A, int64_t lda, const void* Wt, const void* bias, 
     p.g[0].res = reinterpret_cast<const bf16*>(res); p.g[0].ldr = ldo;
     p.g[0].gate = reinterpret_cast<const bf16*>(gate); p.g[0].gate_stride = 0;
     LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
-    launch_gemm(c, cta_group, ma, ma, mb, mb, p);
+    launch_gemm(c, cta_group, bn, ma, ma, mb, mb, p);
   } catch (const Fail& f) {
     return f.code;
   }

@@ -56,6 +56,20 @@ def main():
             ms = timeit(f, flush=flush)
             row[f"cg{cg}_ms"] = ms
             row[f"cg{cg}_tflops"] = 2.0 * M * N * K / ms / 1e9
+        gate = torch.randn(N, device="cuda").to(torch.bfloat16)
+        for bn in (256, 224, 192):
+            os.environ["TFX_OP_LINEAR_BLOCK_N"] = str(bn)
+            def f():
+                _lib.check(lib.tfx_op_linear(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), out.data_ptr(), N, M, N, K, 0, None, None, 2, st))
+            ms = timeit(f, flush=flush)
+            row[f"cg2_bn{bn}_tflops"] = 2.0 * M * N * K / ms / 1e9
+        os.environ.pop("TFX_OP_LINEAR_BLOCK_N")
+        for mode, mname in ((1, "gelu"), (2, "gate_res")):
+            def f():
+                _lib.check(lib.tfx_op_linear(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), out.data_ptr(), N, M, N, K, mode,
+                                             gate.data_ptr(), out.data_ptr(), 2, st))
+            ms = timeit(f, flush=flush)
+            row[f"cg2_{mname}_tflops"] = 2.0 * M * N * K / ms / 1e9
         ms = timeit(lambda: torch.nn.functional.linear(A, W, b), flush=flush)
         row["cublas_ms"] = ms
         row["cublas_tflops"] = 2.0 * M * N * K / ms / 1e9
@@ -79,6 +93,28 @@ def main():
         ms = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), flush=flush)
         row["sdpa_ms"] = ms
         row["sdpa_tflops"] = fl / ms / 1e9
+        print(row, flush=True)
+        res.append(row)
+    for rows, D in [(2560, 3072), (5120, 3072)]:
+        x = torch.randn(rows, D, device="cuda").to(torch.bfloat16)
+        y = torch.empty_like(x)
+        mod = torch.randn(1, 3 * D, device="cuda").to(torch.bfloat16)
+        def f():
+            _lib.check(lib.tfx_op_ln_modulate(x.data_ptr(), y.data_ptr(), rows, D, rows, mod.data_ptr(), 3 * D, 0, D, st))
+        ms = timeit(f, flush=flush)
+        row = {"kernel": "ln_modulate", "rows": rows, "D": D, "us": ms * 1e3, "GBps": 2 * rows * D * 2 / ms / 1e6}
+        print(row, flush=True)
+        res.append(row)
+    if True:
+        Nn, K = 344 * 3072, 3072
+        W = (torch.randn(Nn, K, device="cuda") * 0.02).to(torch.bfloat16)
+        b = torch.zeros(Nn, device="cuda", dtype=torch.bfloat16)
+        xx = torch.randn(1, K, device="cuda").to(torch.bfloat16)
+        oo = torch.empty(1, Nn, device="cuda", dtype=torch.bfloat16)
+        def f():
+            _lib.check(lib.tfx_op_gemv(xx.data_ptr(), 1, K, W.data_ptr(), b.data_ptr(), Nn, oo.data_ptr(), 1, st))
+        ms = timeit(f)
+        row = {"kernel": "gemv_mod", "N": Nn, "K": K, "us": ms * 1e3, "GBps": Nn * K * 2 / ms / 1e6}
         print(row, flush=True)
         res.append(row)
     if args.json:
