@@ -184,7 +184,7 @@ def run_ours(args, h2, w2, T, desc):
                        axes_dims_rope=(16, 56, 56))
     S, B = h2 * w2, 1
     eng = B200FluxTransformer(cfg, synthetic_getter(cfg, 1234, dev), device=dev, gemm_cta_group=args.cta_group,
-                              attn_q_tiles=args.q_tiles)
+                              attn_q_tiles=args.q_tiles, gemm_mcast=args.mcast)
     # ---- synthetic inputs: per-sample seeds; prompt embeds + schedule come from rank 0
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     latents0 = torch.randn(B, S, 64, generator=g, device=dev).to(torch.bfloat16)
@@ -322,7 +322,7 @@ def run_ours(args, h2, w2, T, desc):
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "image_tokens": S, "text_tokens": T,
                        "layers": [cfg.num_layers, cfg.num_single_layers], "parallelism": f"replica x{world}",
                        "l2": "23.8 GB of weights stream through the 126 MB L2 every step (inputs larger than L2)",
-                       "gemm_cta_group": args.cta_group, "attn_q_tiles": args.q_tiles},
+                       "gemm_cta_group": args.cta_group, "gemm_mcast": args.mcast, "attn_q_tiles": args.q_tiles},
             "clocks": clocks, "gpu_launches": launches, "finite": finite,
             "e2e": {"value": total_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof, "cpu_baseline": cpu}
@@ -340,6 +340,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cta-group", type=int, default=2)
     ap.add_argument("--q-tiles", type=int, default=2)
+    ap.add_argument("--mcast", type=int, default=0, help="CTA pairs per cluster sharing A by TMA multicast (0, 2, 4)")
     ap.add_argument("--layers", type=int, default=0, help="debug: override the 19 double blocks (invalidates the number)")
     ap.add_argument("--single-layers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

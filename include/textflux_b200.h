@@ -49,7 +49,7 @@ int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
 void tfx_destroy(tfx_handle h);
 /* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
 const char* tfx_last_error(tfx_handle h);
-/* "gemm_cta_group" (1|2), "attn_q_tiles" (1|2), "use_graph" (0|1), "profile" (0|1: eager launches, one CUDA-event
+/* "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_q_tiles" (1|2), "use_graph" (0|1), "profile" (0|1: eager launches, one CUDA-event
  * pair per kernel, summed per family; resets the sums) */
 int tfx_set_option(tfx_handle h, const char* key, int64_t value);
 /* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step;
@@ -89,7 +89,8 @@ int tfx_step(tfx_handle h, const void* latents_in, const void* cond, const void*
              const void* txt_ids, float sigma, float sigma_next, void* latents_out, void* noise_pred_out, void* stream);
 
 /* ---- single kernels, exported for parity tests against the oracle --------------------------------------------- */
-/* Y = epilogue(A[M,K] W[N,K]^T + bias); mode: 0 store, 1 gelu-tanh, 2 out = res + gate*(.) (gate [N], res [M,N]) */
+/* Y = epilogue(A[M,K] W[N,K]^T + bias); mode: 0 store, 1 gelu-tanh, 2 out = res + gate*(.) (gate [N], res [M,N]);
+ * cta_group: 1 | 2 plain kernels, 22 | 24 multicast kernel with 2 | 4 CTA pairs per cluster */
 int tfx_op_linear(const void* A, int64_t lda, const void* W, const void* bias, void* out, int64_t ldo, int32_t M,
                   int32_t N, int32_t K, int32_t mode, const void* gate, const void* res, int32_t cta_group, void* stream);
 /* q,k,v [B,H,N,dh] -> out rows in the engine's [B*T text rows ; B*S image rows] order, row stride ld_out */

@@ -31,12 +31,13 @@ def _cuda(d):
     return {k: v.cuda() for k, v in d.items()}
 
 
-@pytest.mark.parametrize("cta_group,q_tiles,graph", [(1, 1, False), (1, 2, True), (2, 2, True), (2, 1, False)])
-def test_tiny_forward_vs_reference_golden(golden, cta_group, q_tiles, graph):
+@pytest.mark.parametrize("cta_group,q_tiles,graph,mcast", [(1, 1, False, 0), (1, 2, True, 0), (2, 2, True, 0), (2, 1, False, 0),
+                                                           (2, 2, True, 2), (2, 2, False, 4)])
+def test_tiny_forward_vs_reference_golden(golden, cta_group, q_tiles, graph, mcast):
     g = golden("tiny_forward.pt")
     cfg = fo.FluxConfig(**g["config"])
     sd = fo.init_state_dict(cfg, seed=g["weight_seed"])
-    eng = _engine(cfg, sd, gemm_cta_group=cta_group, attn_q_tiles=q_tiles, use_graph=graph)
+    eng = _engine(cfg, sd, gemm_cta_group=cta_group, attn_q_tiles=q_tiles, use_graph=graph, gemm_mcast=mcast)
     inp = _cuda(g["inputs"])
     hs = torch.cat([inp["latents"], inp["cond"]], dim=2)
     for _ in range(2):  # second call replays the captured graph
@@ -111,15 +112,15 @@ def test_real_dim_blocks_vs_reference_golden(golden):
         ref32 = fo.flux_forward(sd32, cfg, hs.float(), inp["prompt_embeds"].float(), inp["pooled"].float(), t32,
                                 inp["img_ids"].float(), inp["txt_ids"].float(), g32)
     base = _rel(g["sample"], ref32)
-    for cta_group in (1, 2):
-        eng = _engine(cfg, sd, gemm_cta_group=cta_group)
+    for cta_group, mcast in ((1, 0), (2, 0), (2, 2), (2, 4)):
+        eng = _engine(cfg, sd, gemm_cta_group=cta_group, gemm_mcast=mcast)
         d = _cuda(inp)
         out = eng(hidden_states=hs.cuda(), timestep=g["timestep"].cuda(), guidance=g["guidance"].cuda(),
                   pooled_projections=d["pooled"], encoder_hidden_states=d["prompt_embeds"], txt_ids=d["txt_ids"],
                   img_ids=d["img_ids"], return_dict=False)[0]
         torch.cuda.synchronize()
         e16, e32 = _rel(out, g["sample"]), _rel(out, ref32)
-        print(f"real-dim blocks cta_group={cta_group}: ref16-vs-fp32 {base:.3e} engine-vs-ref16 {e16:.3e} engine-vs-fp32 {e32:.3e}")
+        print(f"real-dim blocks cta_group={cta_group} mcast={mcast}: ref16-vs-fp32 {base:.3e} engine-vs-ref16 {e16:.3e} engine-vs-fp32 {e32:.3e}")
         assert e16 <= 2.0 * base and e32 <= 1.5 * base, (e16, e32, base)
         assert _cosdist(out, g["sample"]) < 1e-4
         del eng

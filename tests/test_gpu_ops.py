@@ -88,7 +88,7 @@ SHAPES = [(128, 256, 64), (256, 512, 384), (2560, 3072, 3072), (512, 3072, 4096)
           (200, 768, 1280), (2048, 12288, 3072), (2048, 3072, 15360), (300, 320, 192)]
 
 
-@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
+@pytest.mark.parametrize("cta_group", [1, 2, 22, 24], ids=["cg1", "cg2", "mc2", "mc4"])
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_linear_store(lib, M, N, K, cta_group):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
@@ -101,7 +101,7 @@ def test_linear_store(lib, M, N, K, cta_group):
     assert err < 4e-3, err  # bf16 output rounding ~ 2^-9 relative
 
 
-@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
+@pytest.mark.parametrize("cta_group", [1, 2, 22, 24], ids=["cg1", "cg2", "mc2", "mc4"])
 def test_linear_gelu_and_gate_res(lib, cta_group):
     M, N, K = 384, 1024, 256
     g = torch.Generator(device="cuda").manual_seed(5)
@@ -119,10 +119,12 @@ def test_linear_gelu_and_gate_res(lib, cta_group):
     assert _rel(out, ref) < 4e-3
 
 
-@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
+@pytest.mark.parametrize("cta_group", [1, 2, 22], ids=["cg1", "cg2", "mc2"])
 @pytest.mark.parametrize("bn", [224, 192])
 def test_linear_narrow_tiles(lib, monkeypatch, bn, cta_group):
     """224- and 192-wide tiles (picked by the host against wave quantisation) give the same results."""
+    if cta_group >= 20 and bn == 192:
+        pytest.skip("multicast kernel is instantiated for 256/224-wide tiles")
     monkeypatch.setenv("TFX_OP_LINEAR_BLOCK_N", str(bn))
     for (M, N, K) in [(2560, 3072, 3072), (300, 320, 192), (512, 448, 128)]:
         g = torch.Generator(device="cuda").manual_seed(M + N + K + bn)

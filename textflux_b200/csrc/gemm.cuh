@@ -116,6 +116,125 @@ __device__ __forceinline__ void linear_out(const uint32_t (&v)[32], const __nv_b
   for (int i = 0; i < 32; ++i) x[i] = bf16_round(__uint_as_float(v[i]) + b[i]);
 }
 
+// One thread's share of a tile's epilogue: row m_local of group grp, the column chunks of half `half`.
+// t_acc = TMEM address of the accumulator stage at this warp's lane quadrant.
+template <int kBN>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int grp, int m_local, int n_tile0, uint32_t t_acc,
+                                                   int half, int lane) {
+  constexpr int kChunks = kBN / 32;
+  const GemmGroup& G = p.g[grp];
+  const bool row_ok = m_local < G.M;
+  const int mode = (n_tile0 < p.n_split) ? p.mode0 : p.mode1;
+  const int bidx = m_local / G.rows_per_sample;
+  const int pos = G.pos_offset + (m_local - bidx * G.rows_per_sample);
+  if (mode == EPI_QKV) {
+    const int sect = n_tile0 / p.D;  // 0 q, 1 k, 2 v
+    const int dh = p.head_dim;
+    const int head0 = (n_tile0 - sect * p.D) / dh;
+    const int heads_in_tile = kBN / dh;  // QKV launches use kBN = 256 (host-enforced): 2 or 4 heads per tile
+    const int chunks_per_head = dh / 32;
+    __nv_bfloat16* dst_base = (sect == 0) ? p.q : (sect == 1) ? p.k : p.v;
+    const __nv_bfloat16* rmsw = (sect == 0) ? G.rms_q : G.rms_k;
+    for (int hh = half * (heads_in_tile / 2); hh < (half + 1) * (heads_in_tile / 2); ++hh) {
+      const int head = head0 + hh;
+      if (n_tile0 + hh * dh >= p.N) break;
+      __nv_bfloat16* dst = dst_base + ((long long)(bidx * p.num_heads + head) * p.n_joint + pos) * dh;
+      float rstd = 0.f;
+      if (sect < 2) {
+        float ss = 0.f;
+        for (int c = 0; c < chunks_per_head; ++c) {
+          uint32_t v[32];
+          float x[32];
+          tmem_ld32(t_acc + uint32_t(hh * dh + c * 32), v);
+          tmem_ld_wait();
+          linear_out(v, G.bias, n_tile0 + hh * dh + c * 32, p.N, x);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) ss = fmaf(x[i], x[i], ss);
+        }
+        rstd = rsqrtf(ss / float(dh) + p.rms_eps);
+      }
+      for (int c = 0; c < chunks_per_head; ++c) {
+        uint32_t v[32];
+        float x[32];
+        tmem_ld32(t_acc + uint32_t(hh * dh + c * 32), v);
+        tmem_ld_wait();
+        linear_out(v, G.bias, n_tile0 + hh * dh + c * 32, p.N, x);
+        if (sect < 2) {
+          float w[32];
+          load_bf16x32(rmsw + c * 32, w);
+          // RMSNorm.forward: (x * rsqrt(var+eps)) -> bf16 -> * weight(bf16) -> bf16   (normalization.py:535-546)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = bf16_round(bf16_round(x[i] * rstd) * w[i]);
+          // apply_rotary_emb: fp32 x*cos + rot(x)*sin on interleaved pairs (embeddings.py:904-914)
+          if (row_ok) {
+            const float4* cs4 = reinterpret_cast<const float4*>(p.rope + (long long)pos * (dh / 2) + c * 16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 cs = __ldg(cs4 + i);  // (cos0, sin0, cos1, sin1)
+              float a0 = x[4 * i + 0], a1 = x[4 * i + 1], b0 = x[4 * i + 2], b1 = x[4 * i + 3];
+              x[4 * i + 0] = __fadd_rn(__fmul_rn(a0, cs.x), __fmul_rn(-a1, cs.y));
+              x[4 * i + 1] = __fadd_rn(__fmul_rn(a1, cs.x), __fmul_rn(a0, cs.y));
+              x[4 * i + 2] = __fadd_rn(__fmul_rn(b0, cs.z), __fmul_rn(-b1, cs.w));
+              x[4 * i + 3] = __fadd_rn(__fmul_rn(b1, cs.z), __fmul_rn(b0, cs.w));
+            }
+          }
+        }
+        if (row_ok) store_bf16x32(dst + c * 32, x);
+      }
+    }
+  } else {
+    const int n_out0 = (n_tile0 < p.n_split) ? n_tile0 : (n_tile0 - p.n_split + p.col_offset1);
+    for (int c = half * ((kChunks + 1) / 2); c < (half ? kChunks : (kChunks + 1) / 2); ++c) {
+      const int n = n_tile0 + c * 32;
+      if (n >= p.N) break;  // warp-uniform
+      uint32_t v[32];
+      float x[32];
+      tmem_ld32(t_acc + uint32_t(c * 32), v);
+      tmem_ld_wait();
+      linear_out(v, G.bias, n, p.N, x);
+      const int no = n_out0 + c * 32;
+      if (mode == EPI_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = gelu_tanh(x[i]);
+      } else if (mode == EPI_GATE_RES) {
+        if (row_ok) {
+          float g[32], r[32];
+          load_bf16x32(G.gate + (long long)bidx * G.gate_stride + n, g);
+          load_bf16x32<false>(G.res + (long long)m_local * G.ldr + no, r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = r[i] + bf16_round(g[i] * x[i]);
+        }
+      } else if (mode == EPI_EULER) {
+        if (row_ok) {
+          const float dt = __ldg(p.dt_ptr);
+          if (n + 32 <= p.N) {
+            float r[32], y[32];
+            if (G.out) store_bf16x32(G.out + (long long)m_local * G.ldo + no, x);
+            load_bf16x32<false>(G.res + (long long)m_local * G.ldr + no, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = r[i] + bf16_round(dt * x[i]);
+            store_bf16x32(G.out2 + (long long)m_local * G.ldr + no, y);
+          } else {
+            for (int i = 0; i < 32 && n + i < p.N; ++i) {
+              if (G.out) G.out[(long long)m_local * G.ldo + no + i] = __float2bfloat16_rn(x[i]);
+              float r = __bfloat162float(G.res[(long long)m_local * G.ldr + no + i]);
+              G.out2[(long long)m_local * G.ldr + no + i] = __float2bfloat16_rn(r + bf16_round(dt * x[i]));
+            }
+          }
+        }
+        continue;
+      }
+      if (row_ok) {
+        if (n + 32 <= p.N) {
+          store_bf16x32(G.out + (long long)m_local * G.ldo + no, x);
+        } else {
+          for (int i = 0; i < 32 && n + i < p.N; ++i) G.out[(long long)m_local * G.ldo + no + i] = __float2bfloat16_rn(x[i]);
+        }
+      }
+    }
+  }
+}
+
 template <int kCtaGroup, int kBN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -123,7 +242,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
                     const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<kCtaGroup, kBN>;
   constexpr int kStages = Cfg::kStages;
-  constexpr int kChunks = kBN / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -248,125 +366,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     for (int t = first_tile; t < num_tiles; t += tile_step) {
       const int mi = t % MT, ni = t / MT;
       const int grp = (mi < mt0) ? 0 : 1;
-      const GemmGroup& G = p.g[grp];
       const int m_local = (grp ? mi - mt0 : mi) * Cfg::kTileM + int(cta_rank) * 128 + quad * 32 + lane;
-      const bool row_ok = m_local < G.M;
       const int n_tile0 = ni * kBN;
-      const int mode = (n_tile0 < p.n_split) ? p.mode0 : p.mode1;
-      const int bidx = m_local / G.rows_per_sample;
-      const int pos = G.pos_offset + (m_local - bidx * G.rows_per_sample);
 
       if constexpr (kCtaGroup == 2) mbar_wait_cluster(&tmem_full_bar[acc], acc_phase);
       else mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 256);
 
-      if (mode == EPI_QKV) {
-        const int sect = n_tile0 / p.D;  // 0 q, 1 k, 2 v
-        const int dh = p.head_dim;
-        const int head0 = (n_tile0 - sect * p.D) / dh;
-        const int heads_in_tile = kBN / dh;  // QKV launches use kBN = 256 (host-enforced): 2 or 4 heads per tile
-        const int chunks_per_head = dh / 32;
-        __nv_bfloat16* dst_base = (sect == 0) ? p.q : (sect == 1) ? p.k : p.v;
-        const __nv_bfloat16* rmsw = (sect == 0) ? G.rms_q : G.rms_k;
-        for (int hh = half * (heads_in_tile / 2); hh < (half + 1) * (heads_in_tile / 2); ++hh) {
-          const int head = head0 + hh;
-          if (n_tile0 + hh * dh >= p.N) break;
-          __nv_bfloat16* dst = dst_base + ((long long)(bidx * p.num_heads + head) * p.n_joint + pos) * dh;
-          float rstd = 0.f;
-          if (sect < 2) {
-            float ss = 0.f;
-            for (int c = 0; c < chunks_per_head; ++c) {
-              uint32_t v[32];
-              float x[32];
-              tmem_ld32(t_acc + uint32_t(hh * dh + c * 32), v);
-              tmem_ld_wait();
-              linear_out(v, G.bias, n_tile0 + hh * dh + c * 32, p.N, x);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) ss = fmaf(x[i], x[i], ss);
-            }
-            rstd = rsqrtf(ss / float(dh) + p.rms_eps);
-          }
-          for (int c = 0; c < chunks_per_head; ++c) {
-            uint32_t v[32];
-            float x[32];
-            tmem_ld32(t_acc + uint32_t(hh * dh + c * 32), v);
-            tmem_ld_wait();
-            linear_out(v, G.bias, n_tile0 + hh * dh + c * 32, p.N, x);
-            if (sect < 2) {
-              float w[32];
-              load_bf16x32(rmsw + c * 32, w);
-              // RMSNorm.forward: (x * rsqrt(var+eps)) -> bf16 -> * weight(bf16) -> bf16   (normalization.py:535-546)
-#pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = bf16_round(bf16_round(x[i] * rstd) * w[i]);
-              // apply_rotary_emb: fp32 x*cos + rot(x)*sin on interleaved pairs (embeddings.py:904-914)
-              if (row_ok) {
-                const float4* cs4 = reinterpret_cast<const float4*>(p.rope + (long long)pos * (dh / 2) + c * 16);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  float4 cs = __ldg(cs4 + i);  // (cos0, sin0, cos1, sin1)
-                  float a0 = x[4 * i + 0], a1 = x[4 * i + 1], b0 = x[4 * i + 2], b1 = x[4 * i + 3];
-                  x[4 * i + 0] = __fadd_rn(__fmul_rn(a0, cs.x), __fmul_rn(-a1, cs.y));
-                  x[4 * i + 1] = __fadd_rn(__fmul_rn(a1, cs.x), __fmul_rn(a0, cs.y));
-                  x[4 * i + 2] = __fadd_rn(__fmul_rn(b0, cs.z), __fmul_rn(-b1, cs.w));
-                  x[4 * i + 3] = __fadd_rn(__fmul_rn(b1, cs.z), __fmul_rn(b0, cs.w));
-                }
-              }
-            }
-            if (row_ok) store_bf16x32(dst + c * 32, x);
-          }
-        }
-      } else {
-        const int n_out0 = (n_tile0 < p.n_split) ? n_tile0 : (n_tile0 - p.n_split + p.col_offset1);
-        for (int c = half * ((kChunks + 1) / 2); c < (half ? kChunks : (kChunks + 1) / 2); ++c) {
-          const int n = n_tile0 + c * 32;
-          if (n >= p.N) break;  // warp-uniform
-          uint32_t v[32];
-          float x[32];
-          tmem_ld32(t_acc + uint32_t(c * 32), v);
-          tmem_ld_wait();
-          linear_out(v, G.bias, n, p.N, x);
-          const int no = n_out0 + c * 32;
-          if (mode == EPI_GELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) x[i] = gelu_tanh(x[i]);
-          } else if (mode == EPI_GATE_RES) {
-            if (row_ok) {
-              float g[32], r[32];
-              load_bf16x32(G.gate + (long long)bidx * G.gate_stride + n, g);
-              load_bf16x32<false>(G.res + (long long)m_local * G.ldr + no, r);
-#pragma unroll
-              for (int i = 0; i < 32; ++i) x[i] = r[i] + bf16_round(g[i] * x[i]);
-            }
-          } else if (mode == EPI_EULER) {
-            if (row_ok) {
-              const float dt = __ldg(p.dt_ptr);
-              if (n + 32 <= p.N) {
-                float r[32], y[32];
-                if (G.out) store_bf16x32(G.out + (long long)m_local * G.ldo + no, x);
-                load_bf16x32<false>(G.res + (long long)m_local * G.ldr + no, r);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) y[i] = r[i] + bf16_round(dt * x[i]);
-                store_bf16x32(G.out2 + (long long)m_local * G.ldr + no, y);
-              } else {
-                for (int i = 0; i < 32 && n + i < p.N; ++i) {
-                  if (G.out) G.out[(long long)m_local * G.ldo + no + i] = __float2bfloat16_rn(x[i]);
-                  float r = __bfloat162float(G.res[(long long)m_local * G.ldr + no + i]);
-                  G.out2[(long long)m_local * G.ldr + no + i] = __float2bfloat16_rn(r + bf16_round(dt * x[i]));
-                }
-              }
-            }
-            continue;
-          }
-          if (row_ok) {
-            if (n + 32 <= p.N) {
-              store_bf16x32(G.out + (long long)m_local * G.ldo + no, x);
-            } else {
-              for (int i = 0; i < 32 && n + i < p.N; ++i) G.out[(long long)m_local * G.ldo + no + i] = __float2bfloat16_rn(x[i]);
-            }
-          }
-        }
-      }
+      gemm_epilogue_tile<kBN>(p, grp, m_local, n_tile0, t_acc, half, lane);
       // release this accumulator stage back to the MMA issuer
       tc_fence_before();
       __syncwarp();
@@ -382,6 +390,187 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   tc_fence_before();
   if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
   if (warp == 2) tmem_dealloc<kCtaGroup>(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multicast variant.  The plain 2-CTA kernel above is bound by L2->SM operand traffic (64 B/cycle/SM for 256x256x64
+// tiles, ~6.2 KB/cycle chip-wide measured, profiles/r1a_ncu_summary.md).  Here kPN CTA pairs form one cluster of 2*kPN
+// CTAs and compute kPN horizontally adjacent 256 x kBN tiles: they need the same A rows, so every CTA fetches only
+// 1/kPN of its 128 A rows and TMA-multicasts it to the CTAs of the other pairs that hold the same rows.  Per-CTA
+// traffic per k-block drops from 32 KB to 16/kPN + 16 KB.
+//   * full[s]      per CTA, count 1 (own producer) + tx bytes of the whole stage (A quarters arrive from kPN senders)
+//   * peer_full[s] in each pair leader: the non-leader relays "my stage is full" with one remote arrive
+//   * empty[s]     per CTA, count kPN: every pair leader's tcgen05.commit is multicast to all CTAs of the cluster,
+//                  because a stage is overwritten by remote multicasts as well as by the CTA's own loads
+template <int kBN, int kPN>
+struct GemmMcCfg {
+  static constexpr int kCluster = 2 * kPN;
+  static constexpr int kARowsLoad = 128 / kPN;
+  static constexpr int kABytes = 128 * kGemmBlockK * 2;
+  static constexpr int kBRows = kBN / 2;
+  static constexpr int kBBytes = kBRows * kGemmBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = 6;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 512;
+};
+
+template <int kBN, int kPN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_mc_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                       const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                       const __grid_constant__ GemmParams p) {
+  using Cfg = GemmMcCfg<kBN, kPN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* peer_full_bar = full_bar + kStages;
+  uint64_t* empty_bar = peer_full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = int(rank >> 1);
+  const int r = int(rank & 1);
+  const bool is_leader = r == 0;
+  const uint32_t leader_rank = rank & ~1u;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA0);
+    prefetch_tensormap(&tmB0);
+    if (p.num_groups > 1) {
+      prefetch_tensormap(&tmA1);
+      prefetch_tensormap(&tmB1);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&peer_full_bar[i], 1);
+      mbar_init(&empty_bar[i], kPN);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], kGemmEpiWarps * 2);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<2>(tmem_base_ptr, 512);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  const int mt0 = (p.g[0].M + 255) / 256;
+  const int mt1 = (p.num_groups > 1) ? (p.g[1].M + 255) / 256 : 0;
+  const int MT = mt0 + mt1;
+  const int NT = (p.N + kBN - 1) / kBN;
+  const int NS = (NT + kPN - 1) / kPN;  // super columns of kPN tiles
+  const int num_super = MT * NS;
+  const int KB = p.K / kGemmBlockK;
+  const int first = blockIdx.x / Cfg::kCluster;
+  const int step = gridDim.x / Cfg::kCluster;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer (every CTA) =====================
+    uint16_t a_mask = 0;
+#pragma unroll
+    for (int q = 0; q < kPN; ++q) a_mask |= uint16_t(1u << (2 * q + r));
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = first; t < num_super; t += step) {
+      const int mi = t % MT, ni = (t / MT) * kPN + pair;
+      const int grp = (mi < mt0) ? 0 : 1;
+      const int m0 = (grp ? mi - mt0 : mi) * 256 + r * 128 + pair * Cfg::kARowsLoad;
+      const int n0 = ni * kBN + r * Cfg::kBRows;
+      const CUtensorMap* tA = grp ? &tmA1 : &tmA0;
+      const CUtensorMap* tB = grp ? &tmB1 : &tmB0;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        uint8_t* sa = smem_a + stage * Cfg::kABytes + pair * (Cfg::kARowsLoad * 128);
+        uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+        if constexpr (kPN == 1) tma_load_2d(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, kEvictNormal);
+        else tma_load_2d_mcast(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, a_mask, kEvictNormal);
+        tma_load_2d(tB, &full_bar[stage], sb, kb * kGemmBlockK, n0, kEvictNormal);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 3 && lane == 0) {
+    // ===================== relay: tell the pair leader that this CTA's stage has landed =====================
+    if (!is_leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = first; t < num_super; t += step) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait_cluster(&full_bar[stage], phase);
+          mbar_arrive_cluster(&peer_full_bar[stage], leader_rank);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (pair leaders) =====================
+    if (is_leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, kBN, 0, 0);
+      constexpr uint16_t all_mask = uint16_t((1u << Cfg::kCluster) - 1);
+      const uint16_t pair_mask = uint16_t(3u << (2 * pair));
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = first; t < num_super; t += step) {
+        mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + uint32_t(acc * 256);
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait_cluster(&full_bar[stage], phase);
+          mbar_wait_cluster(&peer_full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes), 16, 1024, kLayoutSW128);
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kGemmBlockK / 16; ++k)
+            umma_ss<2>(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+          umma_commit_2sm(&empty_bar[stage], all_mask);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full_bar[acc], pair_mask);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = first; t < num_super; t += step) {
+      const int mi = t % MT, ni = (t / MT) * kPN + pair;
+      const int grp = (mi < mt0) ? 0 : 1;
+      const int m_local = (grp ? mi - mt0 : mi) * 256 + r * 128 + quad * 32 + lane;
+      mbar_wait_cluster(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(acc * 256);
+      if (ni < NT) gemm_epilogue_tile<kBN>(p, grp, m_local, ni * kBN, t_acc, half, lane);  // phantom tiles only keep the protocol going
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], leader_rank);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();
+  if (warp == 2) tmem_dealloc<2>(tmem_base, 512);
 }
 
 }  // namespace tfx

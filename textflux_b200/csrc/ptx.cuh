@@ -132,6 +132,16 @@ __device__ __forceinline__ void tma_load_2d_2sm(const void* tmap, uint64_t* bar,
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// multicast form: the box lands at the same smem offset, and completes tx bytes on the same-offset barrier, in every
+// CTA of the cluster whose bit is set in `cta_mask`.
+__device__ __forceinline__ void tma_load_2d_mcast(const void* tmap, uint64_t* bar, void* dst, int32_t c0, int32_t c1, uint16_t cta_mask,
+                                                  uint64_t hint) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%4, %5}], [%2], %3, %6;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, void* dst, int32_t c0, int32_t c1, int32_t c2, uint64_t hint) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"

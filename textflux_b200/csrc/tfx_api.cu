@@ -165,6 +165,10 @@ void configure_kernels(std::string* err_) {
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 224>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 192>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 192>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<256, 2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<224, 2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<256, 4>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<224, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<224, 4>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 1>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 1>::kSmemBytes));
@@ -240,6 +244,80 @@ void launch_gemm(const LaunchCtx& c, int cta_group, int block_n, const CUtensorM
   ++*c.counter;
 }
 
+// ---- multicast GEMM: clusters of 2*kPN CTAs (kPN pairs share their A rows)
+template <int kBN, int kPN>
+int max_mc_clusters(int device) {
+  static std::map<int, int> cache;
+  auto it = cache.find(device);
+  if (it != cache.end()) return it->second;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.gridDim = dim3(2 * kPN * 64);
+  cfg.dynamicSmemBytes = GemmMcCfg<kBN, kPN>::kSmemBytes;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2 * kPN;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_mc_tcgen05_kernel<kBN, kPN>, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = num_sms(device) / (2 * kPN) * 3 / 4;  // conservative fallback
+  }
+  cache[device] = n;
+  return n;
+}
+
+template <int kBN, int kPN>
+void launch_gemm_mc_inst(const LaunchCtx& c, long long m_tiles, const CUtensorMap& a0, const CUtensorMap& a1,
+                         const CUtensorMap& b0, const CUtensorMap& b1, const GemmParams& p) {
+  std::string* err_ = c.err_;
+  const long long nt = (p.N + kBN - 1) / kBN;
+  const long long supers = m_tiles * ((nt + kPN - 1) / kPN);
+  long long clusters = max_mc_clusters<kBN, kPN>(c.device);
+  if (supers < clusters) clusters = supers;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.gridDim = dim3((unsigned)(clusters * 2 * kPN));
+  cfg.stream = c.stream;
+  cfg.dynamicSmemBytes = GemmMcCfg<kBN, kPN>::kSmemBytes;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2 * kPN;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_mc_tcgen05_kernel<kBN, kPN>, a0, a1, b0, b1, p));
+}
+
+// a0/a1: descriptors with 128/pn-row boxes; b0/b1: block_n/2-row boxes.
+void launch_gemm_mc(const LaunchCtx& c, int pn, int block_n, const CUtensorMap& a0, const CUtensorMap& a1,
+                    const CUtensorMap& b0, const CUtensorMap& b1, const GemmParams& p) {
+  std::string* err_ = c.err_;
+  REQUIRE(p.K % kGemmBlockK == 0 && p.K > 0, TFX_ERR_INVALID, "GEMM K=%d must be a positive multiple of %d", p.K, kGemmBlockK);
+  REQUIRE(p.n_split == p.N || p.n_split % block_n == 0, TFX_ERR_INVALID, "n_split %d not tile aligned", p.n_split);
+  const bool qkv = p.mode0 == EPI_QKV || (p.n_split < p.N && p.mode1 == EPI_QKV);
+  REQUIRE(!qkv || block_n == 256, TFX_ERR_INVALID, "QKV epilogue needs 256-wide tiles");
+  ProfScope ps(c, KF_GEMM);
+  long long m_tiles = 0;
+  for (int g = 0; g < p.num_groups; ++g) m_tiles += (p.g[g].M + 255) / 256;
+  if (m_tiles == 0) return;
+  const int key = pn * 1000 + block_n;
+  switch (key) {
+    case 2256: launch_gemm_mc_inst<256, 2>(c, m_tiles, a0, a1, b0, b1, p); break;
+    case 2224: launch_gemm_mc_inst<224, 2>(c, m_tiles, a0, a1, b0, b1, p); break;
+    case 4256: launch_gemm_mc_inst<256, 4>(c, m_tiles, a0, a1, b0, b1, p); break;
+    case 4224: launch_gemm_mc_inst<224, 4>(c, m_tiles, a0, a1, b0, b1, p); break;
+    default: REQUIRE(false, TFX_ERR_INVALID, "no multicast GEMM instance for pn %d block_n %d", pn, block_n);
+  }
+  ++*c.counter;
+}
+
 void launch_attention(const LaunchCtx& c, int head_dim, int q_tiles, const CUtensorMap& tq, const CUtensorMap& tk,
                       const CUtensorMap& tv, const AttnParams& p) {
   std::string* err_ = c.err_;
@@ -310,6 +388,7 @@ struct tfx_model {
   long long launches = 0;
   long long graph_nodes = 0;
   int gemm_cta_group = 1;
+  int gemm_mcast = 0;  // 0: plain kernels; 2|4: pairs per cluster sharing A by TMA multicast
   int attn_q_tiles = 2;
   int use_graph = 1;
   int profile = 0;
@@ -332,7 +411,8 @@ struct tfx_model {
   float* dt_dev = nullptr;
   float2* rope = nullptr;
   // activation-side TMA descriptors, [0] text rows, [1] image rows
-  CUtensorMap mA_nbuf[2], mA_attn[2], mA_mlp[2], mA_cat[2], mA_x, mA_enc, mA_final;
+  enum AKind { A_NBUF = 0, A_ATTN = 1, A_MLP = 2, A_CAT = 3, A_X = 4, A_ENC = 5, A_KINDS = 6 };
+  CUtensorMap mA[2][A_KINDS][2];  // [0: 128-row boxes | 1: 128/gemm_mcast-row boxes for the multicast kernels][kind][group]
   CUtensorMap mQ, mK, mV;
   std::map<std::string, CUtensorMap> mB;  // weight-side descriptors, keyed "<weight>#<cta_group>#<block_n>"
 
@@ -345,13 +425,13 @@ struct tfx_model {
     REQUIRE(it != w.end(), TFX_ERR_MISSING, "weight '%s' was never set", name.c_str());
     return it->second;
   }
-  const CUtensorMap& WB(const std::string& name, int block_n = kGemmBlockN) {
-    const std::string key = name + "#" + std::to_string(gemm_cta_group) + "#" + std::to_string(block_n);
+  const CUtensorMap& WB(const std::string& name, int block_n, int cg) {
+    const std::string key = name + "#" + std::to_string(cg) + "#" + std::to_string(block_n);
     auto it = mB.find(key);
     if (it == mB.end()) {
       const Weight& t = W(name);
       REQUIRE(t.cols % kGemmBlockK == 0, TFX_ERR_INVALID, "weight '%s' has K=%lld, not a multiple of %d", name.c_str(), t.cols, kGemmBlockK);
-      it = mB.emplace(key, make_map_2d(err_, t.ptr, t.rows, t.cols, t.cols, block_n / gemm_cta_group)).first;
+      it = mB.emplace(key, make_map_2d(err_, t.ptr, t.rows, t.cols, t.cols, block_n / cg)).first;
     }
     return it->second;
   }
@@ -359,7 +439,8 @@ struct tfx_model {
   int block_n_for(int Nn) const {
     const int tile_m = 128 * gemm_cta_group;
     const long long mt = ((long long)B * T + tile_m - 1) / tile_m + ((long long)B * S + tile_m - 1) / tile_m;
-    return pick_block_n(mt, Nn, num_sms(device) / gemm_cta_group, true);
+    const int bn = pick_block_n(mt, Nn, num_sms(device) / gemm_cta_group, true);
+    return (gemm_mcast >= 2 && bn == 192) ? 256 : bn;
   }
   void free_workspace() {
     for (void* p : allocs) cudaFree(p);
@@ -380,6 +461,17 @@ struct tfx_model {
   long long mod_single(int j, int chunk) const { return ((long long)cfg.num_layers * 12 + (long long)j * 3 + chunk) * D; }
   long long mod_final(int chunk) const { return ((long long)cfg.num_layers * 12 + (long long)cfg.num_single_layers * 3 + chunk) * D; }
 
+  // One GEMM of the step: A operand `kind` (text rows = group 0, image rows = group 1; `ga` picks which group's
+  // descriptor feeds a single-group launch), weights w0/w1, tile width bn.
+  void gemm(const LaunchCtx& c, int bn, AKind kind, const std::string& w0, const std::string& w1, const GemmParams& p, int ga = -1) {
+    const int g0 = ga < 0 ? 0 : ga, g1 = ga < 0 ? 1 : ga;
+    const int nt = (p.N + bn - 1) / bn;
+    if (gemm_mcast >= 2 && nt >= gemm_mcast) {
+      launch_gemm_mc(c, gemm_mcast, bn, mA[1][kind][g0], mA[1][kind][g1], WB(w0, bn, 2), WB(w1, bn, 2), p);
+    } else {
+      launch_gemm(c, gemm_cta_group, bn, mA[0][kind][g0], mA[0][kind][g1], WB(w0, bn, gemm_cta_group), WB(w1, bn, gemm_cta_group), p);
+    }
+  }
   void build_weight_maps();
   void prepare(int B_, int S_, int T_);
   void enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_noise_pred);
@@ -421,15 +513,17 @@ void tfx_model::prepare(int B_, int S_, int T_) {
 
   const long long rt = (long long)B * T, ri = (long long)B * S;
   const long long row0[2] = {0, rt}, rows[2] = {rt, ri};
-  for (int g = 0; g < 2; ++g) {
-    mA_nbuf[g] = make_map_2d(err_, nbuf + row0[g] * D, rows[g], D, D, 128);
-    mA_attn[g] = make_map_2d(err_, cat + row0[g] * 5 * D, rows[g], D, 5LL * D, 128);
-    mA_mlp[g] = make_map_2d(err_, cat + row0[g] * 5 * D + D, rows[g], 4LL * D, 5LL * D, 128);
-    mA_cat[g] = make_map_2d(err_, cat + row0[g] * 5 * D, rows[g], 5LL * D, 5LL * D, 128);
+  for (int v = 0; v < 2; ++v) {
+    const int box = (v == 0 || gemm_mcast < 2) ? 128 : 128 / gemm_mcast;
+    for (int g = 0; g < 2; ++g) {
+      mA[v][A_NBUF][g] = make_map_2d(err_, nbuf + row0[g] * D, rows[g], D, D, box);
+      mA[v][A_ATTN][g] = make_map_2d(err_, cat + row0[g] * 5 * D, rows[g], D, 5LL * D, box);
+      mA[v][A_MLP][g] = make_map_2d(err_, cat + row0[g] * 5 * D + D, rows[g], 4LL * D, 5LL * D, box);
+      mA[v][A_CAT][g] = make_map_2d(err_, cat + row0[g] * 5 * D, rows[g], 5LL * D, 5LL * D, box);
+      mA[v][A_X][g] = make_map_2d(err_, x_in, ri, cfg.in_channels, cfg.in_channels, box);
+      mA[v][A_ENC][g] = make_map_2d(err_, enc_in, rt, cfg.joint_attention_dim, cfg.joint_attention_dim, box);
+    }
   }
-  mA_x = make_map_2d(err_, x_in, ri, cfg.in_channels, cfg.in_channels, 128);
-  mA_enc = make_map_2d(err_, enc_in, rt, cfg.joint_attention_dim, cfg.joint_attention_dim, 128);
-  mA_final = mA_nbuf[1];
   mQ = make_map_3d(err_, q, (long long)B * H, N, dh);
   mK = make_map_3d(err_, k, (long long)B * H, N, dh);
   mV = make_map_3d(err_, v, (long long)B * H, N, dh);
@@ -490,12 +584,12 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     GemmParams p = base_params(D, cfg.joint_attention_dim);
     p.num_groups = 1;
     p.g[0].bias = W("context_embedder.b").ptr; p.g[0].out = hidden; p.g[0].ldo = D;
-    launch_gemm(c, gemm_cta_group, 256, mA_enc, mA_enc, WB("context_embedder.w"), WB("context_embedder.w"), p);
+    gemm(c, 256, A_ENC, "context_embedder.w", "context_embedder.w", p, 0);
     GemmParams px = base_params(D, cfg.in_channels);
     px.num_groups = 1;
     px.g[0] = px.g[1];
     px.g[0].bias = W("x_embedder.b").ptr; px.g[0].out = hidden + rt * D; px.g[0].ldo = D;
-    launch_gemm(c, gemm_cta_group, 256, mA_x, mA_x, WB("x_embedder.w"), WB("x_embedder.w"), px);
+    gemm(c, 256, A_X, "x_embedder.w", "x_embedder.w", px, 0);
   }
   AttnParams ap;
   ap.B = B; ap.H = H; ap.N = N; ap.T = T; ap.S = S;
@@ -524,7 +618,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].rms_q = W(name("d%d.rms_q", i, sfx[g])).ptr;
         p.g[g].rms_k = W(name("d%d.rms_k", i, sfx[g])).ptr;
       }
-      launch_gemm(c, gemm_cta_group, 256, mA_nbuf[0], mA_nbuf[1], WB(name("d%d.qkv_c", i, ".w")), WB(name("d%d.qkv_x", i, ".w")), p);
+      gemm(c, 256, A_NBUF, name("d%d.qkv_c", i, ".w"), name("d%d.qkv_x", i, ".w"), p);
     }
     launch_attention(c, dh, attn_q_tiles, mQ, mK, mV, ap);
     {
@@ -535,7 +629,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].out = hid_g[g]; p.g[g].ldo = D; p.g[g].res = hid_g[g]; p.g[g].ldr = D;
         p.g[g].gate = mod + mod_double(i, g == 0, 2); p.g[g].gate_stride = mod_rows;
       }
-      launch_gemm(c, gemm_cta_group, bn_d, mA_attn[0], mA_attn[1], WB(name("d%d.out_c", i, ".w"), bn_d), WB(name("d%d.out_x", i, ".w"), bn_d), p);
+      gemm(c, bn_d, A_ATTN, name("d%d.out_c", i, ".w"), name("d%d.out_x", i, ".w"), p);
     }
     lp.shift0 = mod_double(i, 1, 3); lp.scale0 = mod_double(i, 1, 4);
     lp.shift1 = mod_double(i, 0, 3); lp.scale1 = mod_double(i, 0, 4);
@@ -547,7 +641,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].bias = W(name("d%d.ff1", i, sfx[g]) + ".b").ptr;
         p.g[g].out = cat_g[g] + D; p.g[g].ldo = 5LL * D;
       }
-      launch_gemm(c, gemm_cta_group, bn_4d, mA_nbuf[0], mA_nbuf[1], WB(name("d%d.ff1_c", i, ".w"), bn_4d), WB(name("d%d.ff1_x", i, ".w"), bn_4d), p);
+      gemm(c, bn_4d, A_NBUF, name("d%d.ff1_c", i, ".w"), name("d%d.ff1_x", i, ".w"), p);
     }
     {
       GemmParams p = base_params(D, 4 * D);
@@ -557,7 +651,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].out = hid_g[g]; p.g[g].ldo = D; p.g[g].res = hid_g[g]; p.g[g].ldr = D;
         p.g[g].gate = mod + mod_double(i, g == 0, 5); p.g[g].gate_stride = mod_rows;
       }
-      launch_gemm(c, gemm_cta_group, bn_d, mA_mlp[0], mA_mlp[1], WB(name("d%d.ff2_c", i, ".w"), bn_d), WB(name("d%d.ff2_x", i, ".w"), bn_d), p);
+      gemm(c, bn_d, A_MLP, name("d%d.ff2_c", i, ".w"), name("d%d.ff2_x", i, ".w"), p);
     }
   }
   // --- 38 x FluxSingleTransformerBlock (transformer_flux.py:715-739) on the joint [text;image] rows (the cat of
@@ -575,8 +669,8 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].rms_k = W(name("s%d.rms_k", j, "")).ptr;
         p.g[g].out = cat_g[g]; p.g[g].ldo = 5LL * D;
       }
-      const CUtensorMap& wb = WB(name("s%d.qkvmlp", j, ".w"));
-      launch_gemm(c, gemm_cta_group, 256, mA_nbuf[0], mA_nbuf[1], wb, wb, p);
+      const std::string wn = name("s%d.qkvmlp", j, ".w");
+      gemm(c, 256, A_NBUF, wn, wn, p);
     }
     launch_attention(c, dh, attn_q_tiles, mQ, mK, mV, ap);
     {
@@ -587,8 +681,8 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].out = hid_g[g]; p.g[g].ldo = D; p.g[g].res = hid_g[g]; p.g[g].ldr = D;
         p.g[g].gate = mod + mod_single(j, 2); p.g[g].gate_stride = mod_rows;
       }
-      const CUtensorMap& wb = WB(name("s%d.out", j, ".w"), bn_d);
-      launch_gemm(c, gemm_cta_group, bn_d, mA_cat[0], mA_cat[1], wb, wb, p);
+      const std::string wn = name("s%d.out", j, ".w");
+      gemm(c, bn_d, A_CAT, wn, wn, p);
     }
   }
   // --- norm_out (AdaLayerNormContinuous: chunk order scale, shift) + proj_out on the image rows (:1200-1203)
@@ -608,7 +702,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     } else {
       p.g[0].out = out_buf; p.g[0].ldo = C;
     }
-    launch_gemm(c, gemm_cta_group, 256, mA_final, mA_final, WB("proj_out.w"), WB("proj_out.w"), p);
+    gemm(c, 256, A_NBUF, "proj_out.w", "proj_out.w", p, 1);
   }
 }
 
@@ -720,6 +814,10 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
   if (k == "gemm_cta_group") {
     REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "gemm_cta_group must be 1 or 2");
     h->gemm_cta_group = (int)value;
+  } else if (k == "gemm_mcast") {
+    REQUIRE(value == 0 || value == 2 || value == 4, TFX_ERR_INVALID, "gemm_mcast must be 0, 2 or 4");
+    h->gemm_mcast = (int)value;
+    h->free_workspace();  // A-side descriptors depend on it: the next tfx_prepare rebuilds them
   } else if (k == "attn_q_tiles") {
     REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
     h->attn_q_tiles = (int)value;
@@ -902,17 +1000,20 @@ int tfx_op_linear(const void* A, int64_t lda, const void* Wt, const void* bias, 
   try {
     REQUIRE(A && Wt && bias && out, TFX_ERR_INVALID, "null argument");
     REQUIRE(mode >= 0 && mode <= 2, TFX_ERR_INVALID, "mode must be 0..2");
-    REQUIRE(cta_group == 1 || cta_group == 2, TFX_ERR_INVALID, "cta_group must be 1 or 2");
+    const int pn = cta_group >= 20 ? cta_group - 20 : 0;  // 22 / 24: multicast kernel with 2 / 4 pairs per cluster
+    REQUIRE(cta_group == 1 || cta_group == 2 || pn == 2 || pn == 4, TFX_ERR_INVALID, "cta_group must be 1, 2, 22 or 24");
     REQUIRE(mode != EPI_GATE_RES || (gate && res), TFX_ERR_INVALID, "gate/res required for mode 2");
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     configure_kernels(err_);
     if (M == 0) return TFX_OK;
+    const int cg = pn ? 2 : cta_group;
     const char* force = getenv("TFX_OP_LINEAR_BLOCK_N");  // tests pin a tile width through this
-    const int bn = force ? atoi(force) : pick_block_n((M + 128 * cta_group - 1) / (128 * cta_group), N, num_sms(dev) / cta_group, true);
+    int bn = force ? atoi(force) : pick_block_n((M + 128 * cg - 1) / (128 * cg), N, num_sms(dev) / cg, true);
+    if (pn && bn == 192) bn = 256;
     REQUIRE(bn == 256 || bn == 224 || bn == 192, TFX_ERR_INVALID, "TFX_OP_LINEAR_BLOCK_N must be 256, 224 or 192");
-    CUtensorMap ma = make_map_2d(err_, A, M, K, lda, 128);
-    CUtensorMap mb = make_map_2d(err_, Wt, N, K, K, bn / cta_group);
+    CUtensorMap ma = make_map_2d(err_, A, M, K, lda, pn ? 128 / pn : 128);
+    CUtensorMap mb = make_map_2d(err_, Wt, N, K, K, bn / cg);
     GemmParams p;
     memset(&p, 0, sizeof p);
     p.N = N; p.K = K; p.num_groups = 1; p.n_split = N; p.mode0 = mode; p.mode1 = mode;
@@ -921,7 +1022,8 @@ int tfx_op_linear(const void* A, int64_t lda, const void* Wt, const void* bias, 
     p.g[0].res = reinterpret_cast<const bf16*>(res); p.g[0].ldr = ldo;
     p.g[0].gate = reinterpret_cast<const bf16*>(gate); p.g[0].gate_stride = 0;
     LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
-    launch_gemm(c, cta_group, bn, ma, ma, mb, mb, p);
+    if (pn) launch_gemm_mc(c, pn, bn, ma, ma, mb, mb, p);
+    else launch_gemm(c, cta_group, bn, ma, ma, mb, mb, p);
   } catch (const Fail& f) {
     return f.code;
   }

@@ -67,7 +67,8 @@ class B200FluxTransformer(torch.nn.Module):
     """
 
     def __init__(self, config, get: Callable[[str], Tensor], device: Union[str, torch.device] = "cuda",
-                 gemm_cta_group: Optional[int] = None, attn_q_tiles: Optional[int] = None, use_graph: bool = True):
+                 gemm_cta_group: Optional[int] = None, attn_q_tiles: Optional[int] = None, use_graph: bool = True,
+                 gemm_mcast: Optional[int] = None):
         super().__init__()
         self._lib = _lib.load()
         dev = torch.device(device)
@@ -94,8 +95,10 @@ class B200FluxTransformer(torch.nn.Module):
             self.set_option("gemm_cta_group", gemm_cta_group)
         if attn_q_tiles is not None:
             self.set_option("attn_q_tiles", attn_q_tiles)
-        self.set_option("use_graph", int(use_graph))
         self._shape: Optional[Tuple[int, int, int]] = None
+        self.set_option("use_graph", int(use_graph))
+        if gemm_mcast is not None:
+            self.set_option("gemm_mcast", gemm_mcast)
 
     # ---- construction helpers -------------------------------------------------------------------------------
     @classmethod
@@ -130,6 +133,8 @@ class B200FluxTransformer(torch.nn.Module):
 
     def set_option(self, key: str, value: int) -> None:
         _lib.check(self._lib.tfx_set_option(self._h, key.encode(), int(value)), self._h)
+        if key == "gemm_mcast":
+            self._shape = None  # the library dropped its workspace; re-run tfx_prepare on the next call
 
     def counter(self, key: str) -> int:
         v = C.c_int64()

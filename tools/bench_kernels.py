@@ -50,7 +50,7 @@ def main():
         b = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
         row = {"kernel": "gemm", "name": name, "M": M, "N": N, "K": K}
-        for cg in (1, 2):
+        for cg in (1, 2, 22, 24):
             def f():
                 _lib.check(lib.tfx_op_linear(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), out.data_ptr(), N, M, N, K, 0, None, None, cg, st))
             ms = timeit(f, flush=flush)
