@@ -58,6 +58,7 @@ struct GemmParams {
   const float2* rope;        // [n_joint, head_dim/2] (cos, sin)
   float rms_eps;
   const float* dt_ptr;  // EULER: device scalar float(bf16(sigma_next - sigma))
+  int debug_flags;      // bring-up experiments (0 in production)
 };
 
 constexpr int kGemmBlockN = 256;  // default tile width; 224 / 192 are instantiated to cut wave quantisation
@@ -398,8 +399,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
 // CTAs and compute kPN horizontally adjacent 256 x kBN tiles: they need the same A rows, so every CTA fetches only
 // 1/kPN of its 128 A rows and TMA-multicasts it to the CTAs of the other pairs that hold the same rows.  Per-CTA
 // traffic per k-block drops from 32 KB to 16/kPN + 16 KB.
-//   * full[s]      per CTA, count 1 (own producer) + tx bytes of the whole stage (A quarters arrive from kPN senders)
-//   * peer_full[s] in each pair leader: the non-leader relays "my stage is full" with one remote arrive
+//   * full[s]      in each pair leader, count 1 (its producer) + tx bytes of BOTH CTAs' stage: all loads use the
+//                  cta_group::2 TMA form, which completes on the destination's pair leader (A quarters arrive from kPN
+//                  senders).  (A first version relayed "peer stage full" with a remote mbarrier arrive per stage; the
+//                  release.cluster arrive serialised the relay thread and halved throughput.)
 //   * empty[s]     per CTA, count kPN: every pair leader's tcgen05.commit is multicast to all CTAs of the cluster,
 //                  because a stage is overwritten by remote multicasts as well as by the CTA's own loads
 template <int kBN, int kPN>
@@ -426,8 +429,7 @@ gemm_mc_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kABytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
-  uint64_t* peer_full_bar = full_bar + kStages;
-  uint64_t* empty_bar = peer_full_bar + kStages;
+  uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
@@ -451,7 +453,6 @@ gemm_mc_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&peer_full_bar[i], 1);
       mbar_init(&empty_bar[i], kPN);
     }
     for (int i = 0; i < 2; ++i) {
@@ -495,26 +496,13 @@ gemm_mc_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
       const CUtensorMap* tB = grp ? &tmB1 : &tmB0;
       for (int kb = 0; kb < KB; ++kb) {
         mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
         uint8_t* sa = smem_a + stage * Cfg::kABytes + pair * (Cfg::kARowsLoad * 128);
         uint8_t* sb = smem_b + stage * Cfg::kBBytes;
-        if constexpr (kPN == 1) tma_load_2d(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, kEvictNormal);
-        else tma_load_2d_mcast(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, a_mask, kEvictNormal);
-        tma_load_2d(tB, &full_bar[stage], sb, kb * kGemmBlockK, n0, kEvictNormal);
+        if constexpr (kPN == 1) tma_load_2d_2sm(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, kEvictNormal);
+        else tma_load_2d_mcast_2sm(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, a_mask, kEvictNormal);
+        tma_load_2d_2sm(tB, &full_bar[stage], sb, kb * kGemmBlockK, n0, kEvictNormal);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
-      }
-    }
-  } else if (warp == 3 && lane == 0) {
-    // ===================== relay: tell the pair leader that this CTA's stage has landed =====================
-    if (!is_leader) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = first; t < num_super; t += step) {
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait_cluster(&full_bar[stage], phase);
-          mbar_arrive_cluster(&peer_full_bar[stage], leader_rank);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-        }
       }
     }
   } else if (warp == 1 && lane == 0) {
@@ -533,7 +521,6 @@ gemm_mc_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
         const uint32_t d_tmem = tmem_base + uint32_t(acc * 256);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait_cluster(&full_bar[stage], phase);
-          mbar_wait_cluster(&peer_full_bar[stage], phase);
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(smem_a + stage * Cfg::kABytes), 16, 1024, kLayoutSW128);
           const uint64_t db = make_smem_desc(smem_u32(smem_b + stage * Cfg::kBBytes), 16, 1024, kLayoutSW128);

@@ -142,6 +142,17 @@ __device__ __forceinline__ void tma_load_2d_mcast(const void* tmap, uint64_t* ba
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "h"(cta_mask), "r"(c0), "r"(c1), "l"(hint)
       : "memory");
 }
+// cta_group::2 multicast: as above, but in every destination CTA the tx bytes complete on the barrier of that CTA's
+// PAIR LEADER (peer bit of the barrier address cleared), like tma_load_2d_2sm does for a single destination.
+__device__ __forceinline__ void tma_load_2d_mcast_2sm(const void* tmap, uint64_t* bar, void* dst, int32_t c0, int32_t c1,
+                                                      uint16_t cta_mask, uint64_t hint) {
+  uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%4, %5}], [%2], %3, %6;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar), "h"(cta_mask), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, void* dst, int32_t c0, int32_t c1, int32_t c2, uint64_t hint) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"

@@ -165,6 +165,7 @@ void configure_kernels(std::string* err_) {
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 224>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 192>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 192>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<256, 1>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<256, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<224, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<256, 4>::kSmemBytes));
@@ -267,6 +268,8 @@ int max_mc_clusters(int device) {
     cudaGetLastError();
     n = num_sms(device) / (2 * kPN) * 3 / 4;  // conservative fallback
   }
+  if (const char* e = getenv("TFX_MC_CLUSTERS")) n = atoi(e);
+  if (getenv("TFX_DEBUG")) fprintf(stderr, "tfx: gemm_mc<%d,%d> max active clusters %d\n", kBN, kPN, n);
   cache[device] = n;
   return n;
 }
@@ -309,6 +312,7 @@ void launch_gemm_mc(const LaunchCtx& c, int pn, int block_n, const CUtensorMap& 
   if (m_tiles == 0) return;
   const int key = pn * 1000 + block_n;
   switch (key) {
+    case 1256: launch_gemm_mc_inst<256, 1>(c, m_tiles, a0, a1, b0, b1, p); break;
     case 2256: launch_gemm_mc_inst<256, 2>(c, m_tiles, a0, a1, b0, b1, p); break;
     case 2224: launch_gemm_mc_inst<224, 2>(c, m_tiles, a0, a1, b0, b1, p); break;
     case 4256: launch_gemm_mc_inst<256, 4>(c, m_tiles, a0, a1, b0, b1, p); break;
@@ -513,15 +517,15 @@ void tfx_model::prepare(int B_, int S_, int T_) {
 
   const long long rt = (long long)B * T, ri = (long long)B * S;
   const long long row0[2] = {0, rt}, rows[2] = {rt, ri};
-  for (int v = 0; v < 2; ++v) {
-    const int box = (v == 0 || gemm_mcast < 2) ? 128 : 128 / gemm_mcast;
+  for (int vi = 0; vi < 2; ++vi) {
+    const int box = (vi == 0 || gemm_mcast < 2) ? 128 : 128 / gemm_mcast;
     for (int g = 0; g < 2; ++g) {
-      mA[v][A_NBUF][g] = make_map_2d(err_, nbuf + row0[g] * D, rows[g], D, D, box);
-      mA[v][A_ATTN][g] = make_map_2d(err_, cat + row0[g] * 5 * D, rows[g], D, 5LL * D, box);
-      mA[v][A_MLP][g] = make_map_2d(err_, cat + row0[g] * 5 * D + D, rows[g], 4LL * D, 5LL * D, box);
-      mA[v][A_CAT][g] = make_map_2d(err_, cat + row0[g] * 5 * D, rows[g], 5LL * D, 5LL * D, box);
-      mA[v][A_X][g] = make_map_2d(err_, x_in, ri, cfg.in_channels, cfg.in_channels, box);
-      mA[v][A_ENC][g] = make_map_2d(err_, enc_in, rt, cfg.joint_attention_dim, cfg.joint_attention_dim, box);
+      mA[vi][A_NBUF][g] = make_map_2d(err_, nbuf + row0[g] * D, rows[g], D, D, box);
+      mA[vi][A_ATTN][g] = make_map_2d(err_, cat + row0[g] * 5 * D, rows[g], D, 5LL * D, box);
+      mA[vi][A_MLP][g] = make_map_2d(err_, cat + row0[g] * 5 * D + D, rows[g], 4LL * D, 5LL * D, box);
+      mA[vi][A_CAT][g] = make_map_2d(err_, cat + row0[g] * 5 * D, rows[g], 5LL * D, 5LL * D, box);
+      mA[vi][A_X][g] = make_map_2d(err_, x_in, ri, cfg.in_channels, cfg.in_channels, box);
+      mA[vi][A_ENC][g] = make_map_2d(err_, enc_in, rt, cfg.joint_attention_dim, cfg.joint_attention_dim, box);
     }
   }
   mQ = make_map_3d(err_, q, (long long)B * H, N, dh);
@@ -1001,7 +1005,7 @@ int tfx_op_linear(const void* A, int64_t lda, const void* Wt, const void* bias, 
     REQUIRE(A && Wt && bias && out, TFX_ERR_INVALID, "null argument");
     REQUIRE(mode >= 0 && mode <= 2, TFX_ERR_INVALID, "mode must be 0..2");
     const int pn = cta_group >= 20 ? cta_group - 20 : 0;  // 22 / 24: multicast kernel with 2 / 4 pairs per cluster
-    REQUIRE(cta_group == 1 || cta_group == 2 || pn == 2 || pn == 4, TFX_ERR_INVALID, "cta_group must be 1, 2, 22 or 24");
+    REQUIRE(cta_group == 1 || cta_group == 2 || pn == 1 || pn == 2 || pn == 4, TFX_ERR_INVALID, "cta_group must be 1, 2, 21, 22 or 24");
     REQUIRE(mode != EPI_GATE_RES || (gate && res), TFX_ERR_INVALID, "gate/res required for mode 2");
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -1021,6 +1025,7 @@ int tfx_op_linear(const void* A, int64_t lda, const void* Wt, const void* bias, 
     p.g[0].out = reinterpret_cast<bf16*>(out); p.g[0].ldo = ldo;
     p.g[0].res = reinterpret_cast<const bf16*>(res); p.g[0].ldr = ldo;
     p.g[0].gate = reinterpret_cast<const bf16*>(gate); p.g[0].gate_stride = 0;
+    if (const char* e = getenv("TFX_GEMM_DEBUG_FLAGS")) p.debug_flags = atoi(e);
     LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
     if (pn) launch_gemm_mc(c, pn, bn, ma, ma, mb, mb, p);
     else launch_gemm(c, cta_group, bn, ma, ma, mb, mb, p);
