@@ -202,9 +202,10 @@ def run_ours(args, h2, w2, T, desc):
     sch.set_timesteps(sigmas=np.linspace(1.0, 1 / n_sched, n_sched), device=dev, mu=mu)
     sig = sch.sigmas.clone()
     if world > 1:
-        # the ONE collective of the job: text embeddings + pooled + sigma schedule from rank 0 (NCCL over NVLink)
-        for t in (prompt, pooled, sig):
-            dist.broadcast(t, src=0)
+        # the ONE collective of the job: text embeddings + pooled + guidance + sigma schedule from rank 0, packed
+        # into a single NCCL broadcast over NVLink (textflux_b200/dist.py)
+        from textflux_b200.dist import broadcast_conditioning
+        prompt, pooled, sig, _ = broadcast_conditioning(prompt, pooled, sig, 30.0, src=0)
     sig_cpu = sig.tolist()
     ts = ((sig[:-1] * 1000)[:, None].expand(-1, B).to(torch.bfloat16) / 1000).contiguous()
     guidance = torch.full([B], 30.0, device=dev, dtype=torch.float32)
