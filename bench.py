@@ -175,6 +175,10 @@ def run_ours(args, h2, w2, T, desc):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # NCCL writes its banner to stdout; keep stdout for the single JSON line by pointing fd 1 at stderr until then
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -327,7 +331,10 @@ def run_ours(args, h2, w2, T, desc):
             "clocks": clocks, "gpu_launches": launches, "finite": finite,
             "e2e": {"value": total_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof, "cpu_baseline": cpu}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
