@@ -221,8 +221,14 @@ def run_ours(args, h2, w2, T, desc):
     prompt_b, pooled_b = prompt.expand(B, -1, -1).contiguous(), pooled.expand(B, -1).contiguous()
 
     def step(i, lat):
+        # step i of an image's schedule; the schedule-wide modulation precompute (tfx_set_schedule, once per image)
+        # is issued at every schedule start, i.e. INSIDE the timed region (the timed loop starts at k = 0)
         k = i % n_sched
-        return eng.step(lat, cond, prompt_b, pooled_b, ts[k], guidance, img_ids, txt_ids, sig_cpu[k], sig_cpu[k + 1])
+        if args.no_schedule:
+            return eng.step(lat, cond, prompt_b, pooled_b, ts[k], guidance, img_ids, txt_ids, sig_cpu[k], sig_cpu[k + 1])
+        if k == 0:
+            eng.set_schedule(ts, guidance, pooled_b, S, T)
+        return eng.step_scheduled(k, lat, cond, prompt_b, img_ids, txt_ids, sig_cpu[k], sig_cpu[k + 1])
 
     def barrier():
         if world > 1:
@@ -242,7 +248,7 @@ def run_ours(args, h2, w2, T, desc):
     barrier()
     e0.record()
     for i in range(args.steps):
-        lat = step(args.warmup + i, lat)
+        lat = step(i, lat)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -261,7 +267,12 @@ def run_ours(args, h2, w2, T, desc):
         k = i % n_sched
         d = {n: host[n].to(dev, non_blocking=True) for n in ("lat", "cond", "prompt", "pooled", "g", "img", "txt")}
         t = host["ts"][k].to(dev, non_blocking=True)
-        new = eng.step(d["lat"], d["cond"], d["prompt"], d["pooled"], t, d["g"], d["img"], d["txt"], sig_cpu[k], sig_cpu[k + 1])
+        if args.no_schedule:
+            new = eng.step(d["lat"], d["cond"], d["prompt"], d["pooled"], t, d["g"], d["img"], d["txt"], sig_cpu[k], sig_cpu[k + 1])
+        else:
+            if k == 0:
+                eng.set_schedule(host["ts"].to(dev, non_blocking=True), d["g"], d["pooled"], S, T)
+            new = eng.step_scheduled(k, d["lat"], d["cond"], d["prompt"], d["img"], d["txt"], sig_cpu[k], sig_cpu[k + 1])
         out_host.copy_(new, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         host["lat"].copy_(out_host)
@@ -327,7 +338,8 @@ def run_ours(args, h2, w2, T, desc):
             "config": {"workload": desc, "batch_per_gpu": B, "global_batch": B * world, "image_tokens": S, "text_tokens": T,
                        "layers": [cfg.num_layers, cfg.num_single_layers], "parallelism": f"replica x{world}",
                        "l2": "23.8 GB of weights stream through the 126 MB L2 every step (inputs larger than L2)",
-                       "gemm_cta_group": args.cta_group, "gemm_mcast": args.mcast, "attn_q_tiles": args.q_tiles},
+                       "gemm_cta_group": args.cta_group, "gemm_mcast": args.mcast, "attn_q_tiles": args.q_tiles,
+                       "modulation": "per step" if args.no_schedule else "precomputed per 30-step schedule inside the timed region"},
             "clocks": clocks, "gpu_launches": launches, "finite": finite,
             "e2e": {"value": total_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof, "cpu_baseline": cpu}
@@ -352,6 +364,7 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="debug: override the 19 double blocks (invalidates the number)")
     ap.add_argument("--single-layers", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-schedule", action="store_true", help="recompute the adaLN modulation every step (drop-in forward semantics)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     h2, w2, T, desc = WORKLOADS[args.workload]

@@ -49,7 +49,7 @@ int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
 void tfx_destroy(tfx_handle h);
 /* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
 const char* tfx_last_error(tfx_handle h);
-/* "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_q_tiles" (1|2), "use_graph" (0|1), "profile" (0|1: eager launches, one CUDA-event
+/* "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1|2), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "profile" (0|1: eager launches, one CUDA-event
  * pair per kernel, summed per family; resets the sums) */
 int tfx_set_option(tfx_handle h, const char* key, int64_t value);
 /* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step;
@@ -88,12 +88,24 @@ int tfx_step(tfx_handle h, const void* latents_in, const void* cond, const void*
              const void* pooled, const void* timestep_bf16, const void* guidance_f32, const void* img_ids,
              const void* txt_ids, float sigma, float sigma_next, void* latents_out, void* noise_pred_out, void* stream);
 
+/* Hoists the step-invariant part of the loop: computes temb and all adaLN modulation vectors for every step of a
+ * schedule at once (timesteps [n_steps, B] bf16 = t/1000 as the pipeline would pass them per step;
+ * embeddings.py:1327-1339 + normalization.py:167,200,363).  Then tfx_step_scheduled(i) is tfx_step for step i without
+ * the per-step pass over the 6.5 GB modulation matrix.  Results are bit-identical to tfx_step. */
+int tfx_set_schedule(tfx_handle h, const void* timesteps_bf16, int32_t n_steps, const void* guidance_f32, const void* pooled,
+                     void* stream);
+int tfx_step_scheduled(tfx_handle h, int32_t step_index, const void* latents_in, const void* cond,
+                       const void* encoder_hidden_states, const void* img_ids, const void* txt_ids, float sigma,
+                       float sigma_next, void* latents_out, void* noise_pred_out, void* stream);
+
 /* ---- single kernels, exported for parity tests against the oracle --------------------------------------------- */
 /* Y = epilogue(A[M,K] W[N,K]^T + bias); mode: 0 store, 1 gelu-tanh, 2 out = res + gate*(.) (gate [N], res [M,N]);
  * cta_group: 1 | 2 plain kernels, 22 | 24 multicast kernel with 2 | 4 CTA pairs per cluster */
 int tfx_op_linear(const void* A, int64_t lda, const void* W, const void* bias, void* out, int64_t ldo, int32_t M,
                   int32_t N, int32_t K, int32_t mode, const void* gate, const void* res, int32_t cta_group, void* stream);
-/* q,k,v [B,H,N,dh] -> out rows in the engine's [B*T text rows ; B*S image rows] order, row stride ld_out */
+/* q,k,v [B,H,N,dh] -> out rows in the engine's [B*T text rows ; B*S image rows] order, row stride ld_out;
+ * q_tiles = 3: QK-ahead schedule (default in the engine); else v1 schedule with q_tiles = tiles + 10 * emu
+ * (emu = exponentials per 8 evaluated by the FMA-pipe polynomial: 0, 2, 3, 4) */
 int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int64_t ld_out, int32_t B, int32_t H,
                      int32_t T, int32_t S, int32_t head_dim, int32_t q_tiles, void* stream);
 /* y = LN(x)*(1+scale)+shift per row; mod [B, mod_stride]; rows = B*rows_per_sample */

@@ -38,6 +38,7 @@ def test_tiny_forward_vs_reference_golden(golden, cta_group, q_tiles, graph, mca
     cfg = fo.FluxConfig(**g["config"])
     sd = fo.init_state_dict(cfg, seed=g["weight_seed"])
     eng = _engine(cfg, sd, gemm_cta_group=cta_group, attn_q_tiles=q_tiles, use_graph=graph, gemm_mcast=mcast)
+    eng.set_option("attn_variant", 1 if mcast == 0 and cta_group == 1 else 2)  # cover both attention schedules
     inp = _cuda(g["inputs"])
     hs = torch.cat([inp["latents"], inp["cond"]], dim=2)
     for _ in range(2):  # second call replays the captured graph
@@ -93,6 +94,10 @@ def test_tiny_loop_dropin_and_fused(golden):
     for a, b in zip(lat_a, seen):
         assert torch.equal(a, b)
     assert torch.equal(final, lat_a[-1])
+    # per-step modulation (no schedule precompute) gives the same bits
+    final2 = eng.denoise(inp["latents"], inp["cond"], inp["prompt_embeds"], inp["pooled"], inp["txt_ids"], inp["img_ids"],
+                         g["guidance_scale"], n, precompute_modulation=False)
+    assert torch.equal(final2, final)
     for i in range(n):
         assert _cosdist(lat_a[i], g["latents"][i]) < 1e-4, i
         assert _rel(lat_a[i], g["latents"][i]) < 2e-2, i
@@ -164,6 +169,21 @@ def test_full_width_reduced_depth_vs_oracle():
     e16 = _rel(out, ref16)
     print(f"full-width 2+2: engine-vs-oracle-bf16 rel-L2 {e16:.3e} cosdist {_cosdist(out, ref16):.2e}")
     assert e16 < 1.2e-2 and _cosdist(out, ref16) < 1e-4
+
+
+def test_schedule_precompute_batch_and_long_schedule():
+    """tfx_set_schedule over 11 steps x 3 samples (33 rows -> 5 GEMV passes) equals the per-step path bit-for-bit."""
+    cfg = fo.TINY
+    sd = fo.init_state_dict(cfg, seed=9)
+    eng = _engine(cfg, sd)
+    inp = _cuda(fo.synthetic_inputs(cfg, 4, 6, 16, batch=3, seed0=50))
+    a = eng.denoise(inp["latents"], inp["cond"], inp["prompt_embeds"], inp["pooled"], inp["txt_ids"], inp["img_ids"], 3.5, 11)
+    b = eng.denoise(inp["latents"], inp["cond"], inp["prompt_embeds"], inp["pooled"], inp["txt_ids"], inp["img_ids"], 3.5, 11,
+                    precompute_modulation=False)
+    torch.cuda.synchronize()
+    assert torch.isfinite(a.float()).all() and torch.equal(a, b)
+    with pytest.raises(Exception):
+        eng.step_scheduled(11, inp["latents"], inp["cond"], inp["prompt_embeds"], inp["img_ids"], inp["txt_ids"], 0.5, 0.4)
 
 
 def test_engine_input_validation():

@@ -44,8 +44,27 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <int kHeadDim, int kQTiles>
-__global__ void __launch_bounds__(AttnCfg<kHeadDim, kQTiles>::kThreads, 1)
+// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.6e-5, far below
+// the bf16 rounding of P): the softmax is bound by the 16/clk/SM MUFU.EX2 rate, so a fraction of the exponentials is
+// taken off the XU pipe.  x <= ~8 here (scores minus the lazily updated row maximum).
+__device__ __forceinline__ float ex2_emu(float x) {
+  x = fmaxf(x, -125.0f);
+  const float kMagic = 12582912.0f;  // 1.5 * 2^23: adding it rounds x to the nearest integer in the low mantissa bits
+  const float xr = x + kMagic;
+  const float f = x - (xr - kMagic);  // [-0.5, 0.5]
+  const float pf = fmaf(fmaf(fmaf(0.05520550534f, f, 0.24261397123f), f, 0.69325476885f), f, 0.99992769957f);
+  return __int_as_float(__float_as_int(pf) + (__float_as_int(xr) << 23));  // * 2^round(x)
+}
+
+// kEmu of every 8 exponentials go through ex2_emu (0 = all on MUFU)
+template <int kEmu>
+__device__ __forceinline__ bool emu_slot(int i) {
+  const int r = i & 7;
+  return (kEmu >= 1 && r == 7) || (kEmu >= 2 && r == 3) || (kEmu >= 3 && r == 5) || (kEmu >= 4 && r == 1);
+}
+
+template <int kHeadDim, int kQTiles, int kEmu>
+__global__ void __launch_bounds__(AttnCfg<kHeadDim, kQTiles>::kThreads, 1)  // 10 warps = 3 on one SMSP -> 168 regs/thread
 attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<kHeadDim, kQTiles>;
@@ -212,15 +231,31 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const float mc = m_new * c;
       float sum0 = 0.f, sum1 = 0.f;
       uint32_t pk[2][32];
+      if (kEmu > 0 && valid >= 128) {
 #pragma unroll
-      for (int cch = 0; cch < 4; ++cch) {
+        for (int cch = 0; cch < 4; ++cch) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(sr[cch][i]), c, -mc));
-          const float p1 = ex2(fmaf(__uint_as_float(sr[cch][i + 1]), c, -mc));
-          sum0 += p0;
-          sum1 += p1;
-          pk[cch >> 1][(cch & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
+          for (int i = 0; i < 32; i += 2) {
+            const float x0 = fmaf(__uint_as_float(sr[cch][i]), c, -mc);
+            const float x1 = fmaf(__uint_as_float(sr[cch][i + 1]), c, -mc);
+            const float p0 = emu_slot<kEmu>(i) ? ex2_emu(x0) : ex2(x0);
+            const float p1 = emu_slot<kEmu>(i + 1) ? ex2_emu(x1) : ex2(x1);
+            sum0 += p0;
+            sum1 += p1;
+            pk[cch >> 1][(cch & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int cch = 0; cch < 4; ++cch) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2(fmaf(__uint_as_float(sr[cch][i]), c, -mc));
+            const float p1 = ex2(fmaf(__uint_as_float(sr[cch][i + 1]), c, -mc));
+            sum0 += p0;
+            sum1 += p1;
+            pk[cch >> 1][(cch & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
+          }
         }
       }
       tmem_st32(t_s + 0, pk[0]);  // P (bf16 pairs) over the S columns just consumed
@@ -278,6 +313,258 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Version 2 of the schedule ("QK-ahead").  In the kernel above a query tile's chain is strictly
+//   softmax(j) -> PV(j), QK(j+1) -> softmax(j+1): softmax warps and the tensor pipe wait on each other (ncu: 31 % of
+// warp samples sit in the wait for S, tensor pipe 46 % busy, profiles/r1d).  Here KV tiles are 64 keys, so the
+// 512 TMEM columns hold TWO score buffers per query tile (2 q-tiles x 2 x 64) next to the two O accumulators
+// (2 x 128), and the issuer runs QK two tiles ahead: S(j+1) is already in TMEM when softmax(j) finishes, the softmax
+// warpgroups run back to back and the MMAs (PV(j), QK(j+2)) execute in their shadow.
+template <int kHeadDim>
+struct Attn2Cfg {
+  static constexpr int kHalves = kHeadDim / 64;
+  static constexpr int kQBytes = 128 * kHeadDim * 2;   // one 128-row query tile
+  static constexpr int kKvRows = 64;
+  static constexpr int kKvBytes = kKvRows * kHeadDim * 2;  // one K (or V) tile
+  static constexpr int kStages = 4;
+  static constexpr int kThreads = 64 + 256;
+  static constexpr int kSmemBytes = 2 * kQBytes + kStages * 2 * kKvBytes + 1024 + 256;
+  static constexpr int kOCol = 256;  // S[q][b] at (q*2+b)*64, O_q at 256 + q*128
+};
+
+template <int kHeadDim>
+__global__ void __launch_bounds__(Attn2Cfg<kHeadDim>::kThreads, 1)
+attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
+  using Cfg = Attn2Cfg<kHeadDim>;
+  constexpr int kHalves = Cfg::kHalves;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int kQHalfBytes = 128 * 128;  // 128 rows x 128 B
+  constexpr int kKvHalfBytes = 64 * 128;  // 64 rows x 128 B
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                           // [2][kHalves][128][64]
+  uint8_t* sK = sQ + 2 * Cfg::kQBytes;          // [stages][kHalves][64][64]
+  uint8_t* sV = sK + kStages * Cfg::kKvBytes;   // [stages][kHalves][64 kv][64 dh]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * Cfg::kKvBytes);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* k_full = q_full + 1;           // [stages]
+  uint64_t* v_full = k_full + kStages;     // [stages]
+  uint64_t* kv_empty = v_full + kStages;   // [stages]
+  uint64_t* s_full = kv_empty + kStages;   // [2 q][2 buffers]
+  uint64_t* p_full = s_full + 4;           // [2]
+  uint64_t* pv_done = p_full + 2;          // [2]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int bh = b * p.H + head;
+  const int n_kv = (p.N + 63) / 64;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmQ);
+    prefetch_tensormap(&tmK);
+    prefetch_tensormap(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(tmem_base_ptr, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_ptr;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    mbar_arrive_expect_tx(q_full, 2 * Cfg::kQBytes);
+    for (int q = 0; q < 2; ++q)
+      for (int h = 0; h < kHalves; ++h)
+        tma_load_3d(&tmQ, q_full, sQ + q * Cfg::kQBytes + h * kQHalfBytes, h * 64, q0 + q * 128, bh, kEvictFirst);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      mbar_arrive_expect_tx(&k_full[stage], Cfg::kKvBytes);
+      for (int h = 0; h < kHalves; ++h)
+        tma_load_3d(&tmK, &k_full[stage], sK + stage * Cfg::kKvBytes + h * kKvHalfBytes, h * 64, j * 64, bh, kEvictLast);
+      mbar_arrive_expect_tx(&v_full[stage], Cfg::kKvBytes);
+      for (int h = 0; h < kHalves; ++h)
+        tma_load_3d(&tmV, &v_full[stage], sV + stage * Cfg::kKvBytes + h * kKvHalfBytes, h * 64, j * 64, bh, kEvictLast);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, kHeadDim, 0, 1);
+    auto issue_qk = [&](int q, int j) {
+      const int stage = j % kStages;
+      const uint32_t a0 = smem_u32(sQ + q * Cfg::kQBytes);
+      const uint32_t b0 = smem_u32(sK + stage * Cfg::kKvBytes);
+      const uint32_t d = tmem_base + uint32_t((q * 2 + (j & 1)) * 64);
+#pragma unroll
+      for (int kk = 0; kk < kHeadDim / 16; ++kk) {
+        umma_ss<1>(d, make_smem_desc(a0 + uint32_t((kk / 4) * kQHalfBytes + (kk % 4) * 32), 16, 1024, kLayoutSW128),
+                   make_smem_desc(b0 + uint32_t((kk / 4) * kKvHalfBytes + (kk % 4) * 32), 16, 1024, kLayoutSW128), idesc_qk, kk != 0);
+      }
+      umma_commit(&s_full[q * 2 + (j & 1)]);
+    };
+    auto issue_pv = [&](int q, int j) {
+      const int stage = j % kStages;
+      const uint32_t v0 = smem_u32(sV + stage * Cfg::kKvBytes);
+      const uint32_t pcol = tmem_base + uint32_t((q * 2 + (j & 1)) * 64);
+#pragma unroll
+      for (int kk = 0; kk < 64 / 16; ++kk) {
+        umma_ts(tmem_base + uint32_t(Cfg::kOCol + q * 128), pcol + uint32_t(kk * 8),
+                make_smem_desc(v0 + kk * 2048, kKvHalfBytes, 1024, kLayoutSW128), idesc_pv, (j | kk) != 0);
+      }
+      umma_commit(&pv_done[q]);
+    };
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < 2 && j < n_kv; ++j) {  // run two KV tiles ahead
+      mbar_wait(&k_full[j % kStages], 0);
+      tc_fence_after();
+      issue_qk(0, j);
+      issue_qk(1, j);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int stage = j % kStages;
+      mbar_wait(&v_full[stage], (j / kStages) & 1);
+      for (int q = 0; q < 2; ++q) {
+        mbar_wait(&p_full[q], j & 1);
+        tc_fence_after();
+        issue_pv(q, j);
+        if (j + 2 < n_kv) {
+          if (q == 0) { mbar_wait(&k_full[(j + 2) % kStages], ((j + 2) / kStages) & 1); tc_fence_after(); }
+          issue_qk(q, j + 2);  // overwrites S[q][j&1] = P(q,j): ordered behind PV(q,j) by the in-order tensor pipe
+        }
+      }
+      umma_commit(&kv_empty[stage]);
+    }
+  } else if (warp >= 2) {
+    // ===================== softmax warpgroups: one thread per query row =====================
+    const int q = (warp - 2) >> 2;
+    const int quad = warp & 3;
+    const int pos = q0 + q * 128 + quad * 32 + lane;
+    const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16);
+    const uint32_t t_o = t_lane + uint32_t(Cfg::kOCol + q * 128);
+    const float c = p.scale_log2;
+    const float kRescaleThreshold = 8.0f;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int valid = p.N - j * 64;
+      const uint32_t t_s = t_lane + uint32_t((q * 2 + (j & 1)) * 64);
+      mbar_wait(&s_full[q * 2 + (j & 1)], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sr[2][32];
+      tmem_ld32(t_s, sr[0]);
+      tmem_ld32(t_s + 32, sr[1]);
+      tmem_ld_wait();
+      if (valid < 64) {
+#pragma unroll
+        for (int cch = 0; cch < 2; ++cch)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cch * 32 + i >= valid) sr[cch][i] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+      }
+      const float mx = fmaxf(mx0, mx1);
+      const bool need = (mx - m) * c > kRescaleThreshold;
+      const float m_new = need ? mx : m;
+      const float alpha = need ? ex2((m - m_new) * c) : 1.0f;
+      const float mc = m_new * c;
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int cch = 0; cch < 2; ++cch) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(sr[cch][i]), c, -mc));
+          const float p1 = ex2(fmaf(__uint_as_float(sr[cch][i + 1]), c, -mc));
+          sum0 += p0;
+          sum1 += p1;
+          pk[cch * 16 + (i >> 1)] = pack_bf16(p0, p1);
+        }
+      }
+      tmem_st32(t_s, pk);
+      l = l * alpha + (sum0 + sum1);
+      m = m_new;
+      tmem_st_wait();
+      if (j > 0) {
+        // Wait for PV(q, j-1) every iteration: (1) O may only be rescaled once it has landed (PV(q, j) cannot start
+        // before p_full below); (2) it keeps this warpgroup at most one phase ahead of the issuer on p_full -- with
+        // S double-buffered the softmax could otherwise complete two phases before the issuer looks, and an mbarrier
+        // parity wait cannot tell phase k from phase k+2.
+        mbar_wait(&pv_done[q], (j - 1) & 1);
+        tc_fence_after();
+      }
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+#pragma unroll 1
+        for (int cch = 0; cch < kHeadDim / 32; ++cch) {
+          uint32_t v[32];
+          tmem_ld32(t_o + cch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st32(t_o + cch * 32, v);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[q]);
+    }
+    mbar_wait(&pv_done[q], (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const bool row_ok = pos < p.N;
+    const long long row = (pos < p.T) ? (long long)b * p.T + pos : (long long)p.B * p.T + (long long)b * p.S + (pos - p.T);
+    __nv_bfloat16* dst = p.out + row * p.ld_out + head * kHeadDim;
+#pragma unroll 1
+    for (int cch = 0; cch < kHeadDim / 32; ++cch) {
+      uint32_t v[32];
+      tmem_ld32(t_o + cch * 32, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst + cch * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(v[8 * i + 0]) * inv_l, __uint_as_float(v[8 * i + 1]) * inv_l);
+          u.y = pack_bf16(__uint_as_float(v[8 * i + 2]) * inv_l, __uint_as_float(v[8 * i + 3]) * inv_l);
+          u.z = pack_bf16(__uint_as_float(v[8 * i + 4]) * inv_l, __uint_as_float(v[8 * i + 5]) * inv_l);
+          u.w = pack_bf16(__uint_as_float(v[8 * i + 6]) * inv_l, __uint_as_float(v[8 * i + 7]) * inv_l);
+          d4[i] = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<1>(tmem_base, 512);
 }
 
 }  // namespace tfx

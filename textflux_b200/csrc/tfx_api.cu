@@ -91,13 +91,13 @@ CUtensorMap make_map_2d(std::string* err_, const void* ptr, long long rows, long
   return m;
 }
 
-// 3-D bf16 [outer, rows, cols] contiguous; box = [1, 128 rows, 64 cols]
-CUtensorMap make_map_3d(std::string* err_, const void* ptr, long long outer, long long rows, long long cols) {
+// 3-D bf16 [outer, rows, cols] contiguous; box = [1, box_rows rows, 64 cols]
+CUtensorMap make_map_3d(std::string* err_, const void* ptr, long long outer, long long rows, long long cols, int box_rows = 128) {
   CUtensorMap m;
   memset(&m, 0, sizeof m);
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)outer};
   cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = get_encode_fn(err_)(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -170,10 +170,16 @@ void configure_kernels(std::string* err_) {
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<224, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<256, 4>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<224, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<224, 4>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 1>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 1>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 1>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<64>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 1>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 2>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   done = true;
 }
@@ -322,21 +328,46 @@ void launch_gemm_mc(const LaunchCtx& c, int pn, int block_n, const CUtensorMap& 
   ++*c.counter;
 }
 
-void launch_attention(const LaunchCtx& c, int head_dim, int q_tiles, const CUtensorMap& tq, const CUtensorMap& tk,
+// q_tiles: 1 | 2 query tiles per CTA; emu: exponentials per 8 evaluated on the FMA pipe (0, 2, 3, 4; q_tiles == 2 only)
+void launch_attention(const LaunchCtx& c, int head_dim, int q_tiles, int emu, const CUtensorMap& tq, const CUtensorMap& tk,
                       const CUtensorMap& tv, const AttnParams& p) {
   std::string* err_ = c.err_;
   REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
   REQUIRE(q_tiles == 1 || q_tiles == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
   ProfScope ps(c, KF_ATTN);
   dim3 grid((p.N + 128 * q_tiles - 1) / (128 * q_tiles), p.H, p.B);
-  if (head_dim == 128 && q_tiles == 2)
-    attention_tcgen05_kernel<128, 2><<<grid, AttnCfg<128, 2>::kThreads, AttnCfg<128, 2>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
-  else if (head_dim == 128)
-    attention_tcgen05_kernel<128, 1><<<grid, AttnCfg<128, 1>::kThreads, AttnCfg<128, 1>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
-  else if (q_tiles == 2)
-    attention_tcgen05_kernel<64, 2><<<grid, AttnCfg<64, 2>::kThreads, AttnCfg<64, 2>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
+#define TFX_ATTN(DH, QT, EMU) \
+  attention_tcgen05_kernel<DH, QT, EMU><<<grid, AttnCfg<DH, QT>::kThreads, AttnCfg<DH, QT>::kSmemBytes, c.stream>>>(tq, tk, tv, p)
+  if (head_dim == 128 && q_tiles == 2) {
+    switch (emu) {
+      case 2: TFX_ATTN(128, 2, 2); break;
+      case 3: TFX_ATTN(128, 2, 3); break;
+      case 4: TFX_ATTN(128, 2, 4); break;
+      default: TFX_ATTN(128, 2, 0); break;
+    }
+  } else if (head_dim == 128) {
+    TFX_ATTN(128, 1, 0);
+  } else if (q_tiles == 2) {
+    if (emu) TFX_ATTN(64, 2, 3); else TFX_ATTN(64, 2, 0);
+  } else {
+    TFX_ATTN(64, 1, 0);
+  }
+#undef TFX_ATTN
+  CUDA_TRY(cudaGetLastError());
+  ++*c.counter;
+}
+
+// "QK-ahead" schedule: 256 query rows per CTA, 64-key tiles; tk/tv must be descriptors with 64-row boxes
+void launch_attention2(const LaunchCtx& c, int head_dim, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnParams& p) {
+  std::string* err_ = c.err_;
+  REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
+  ProfScope ps(c, KF_ATTN);
+  dim3 grid((p.N + 255) / 256, p.H, p.B);
+  if (head_dim == 128)
+    attention2_tcgen05_kernel<128><<<grid, Attn2Cfg<128>::kThreads, Attn2Cfg<128>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
   else
-    attention_tcgen05_kernel<64, 1><<<grid, AttnCfg<64, 1>::kThreads, AttnCfg<64, 1>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
+    attention2_tcgen05_kernel<64><<<grid, Attn2Cfg<64>::kThreads, Attn2Cfg<64>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
   CUDA_TRY(cudaGetLastError());
   ++*c.counter;
 }
@@ -394,6 +425,8 @@ struct tfx_model {
   int gemm_cta_group = 1;
   int gemm_mcast = 0;  // 0: plain kernels; 2|4: pairs per cluster sharing A by TMA multicast
   int attn_q_tiles = 2;
+  int attn_variant = 1;  // 1: v1 schedule (attn_q_tiles, attn_emu apply); 2: QK-ahead schedule (measured slower)
+  int attn_emu = 0;  // exponentials per 8 evaluated on the FMA pipe instead of MUFU (measured slower: softmax is not XU-bound)
   int use_graph = 1;
   int profile = 0;
   Profiler prof;
@@ -417,12 +450,17 @@ struct tfx_model {
   // activation-side TMA descriptors, [0] text rows, [1] image rows
   enum AKind { A_NBUF = 0, A_ATTN = 1, A_MLP = 2, A_CAT = 3, A_X = 4, A_ENC = 5, A_KINDS = 6 };
   CUtensorMap mA[2][A_KINDS][2];  // [0: 128-row boxes | 1: 128/gemm_mcast-row boxes for the multicast kernels][kind][group]
-  CUtensorMap mQ, mK, mV;
+  CUtensorMap mQ, mK, mV, mK64, mV64;  // 128-row boxes (v1 schedule) and 64-row K/V boxes (QK-ahead schedule)
   std::map<std::string, CUtensorMap> mB;  // weight-side descriptors, keyed "<weight>#<cta_group>#<block_n>"
 
   cudaStream_t stream = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
-  cudaGraphExec_t graph_fwd = nullptr, graph_step = nullptr;
+  cudaGraphExec_t graphs[4] = {nullptr, nullptr, nullptr, nullptr};  // [fused_euler * 2 + scheduled]
+  long long graph_kernels[4] = {0, 0, 0, 0};
+  // schedule-wide modulation table (tfx_set_schedule): [sched_steps * B, mod_rows]
+  bf16* mod_table = nullptr;
+  int sched_steps = 0;
+  bf16 *sched_g = nullptr, *sched_pooled = nullptr;
 
   const Weight& W(const std::string& name) {
     auto it = w.find(name);
@@ -446,11 +484,18 @@ struct tfx_model {
     const int bn = pick_block_n(mt, Nn, num_sms(device) / gemm_cta_group, true);
     return (gemm_mcast >= 2 && bn == 192) ? 256 : bn;
   }
+  void drop_graphs() {
+    for (int i = 0; i < 4; ++i)
+      if (graphs[i]) { cudaGraphExecDestroy(graphs[i]); graphs[i] = nullptr; }
+  }
   void free_workspace() {
     for (void* p : allocs) cudaFree(p);
     allocs.clear();
-    if (graph_fwd) { cudaGraphExecDestroy(graph_fwd); graph_fwd = nullptr; }
-    if (graph_step) { cudaGraphExecDestroy(graph_step); graph_step = nullptr; }
+    drop_graphs();
+    if (mod_table) { cudaFree(mod_table); mod_table = nullptr; }
+    if (sched_g) { cudaFree(sched_g); sched_g = nullptr; }
+    if (sched_pooled) { cudaFree(sched_pooled); sched_pooled = nullptr; }
+    sched_steps = 0;
     B = S = T = N = 0;
   }
   template <typename Tp>
@@ -478,8 +523,9 @@ struct tfx_model {
   }
   void build_weight_maps();
   void prepare(int B_, int S_, int T_);
-  void enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_noise_pred);
-  void run(bool fused_euler, bool want_noise_pred);
+  void enqueue_modulation(const LaunchCtx& c, const bf16* t_rows, const float* g_rows, const bf16* pooled_rows, int rows, bf16* mod_out);
+  void enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_noise_pred, bool scheduled);
+  void run(bool fused_euler, bool want_noise_pred, bool scheduled);
 };
 
 void tfx_model::build_weight_maps() { mB.clear(); }
@@ -506,9 +552,9 @@ void tfx_model::prepare(int B_, int S_, int T_) {
   dt_dev = alloc<float>(4);
   ids_txt = alloc<bf16>((long long)T * 3);
   ids_img = alloc<bf16>((long long)S * 3);
-  tproj = alloc<bf16>((long long)B * 256);
-  h1 = alloc<bf16>((long long)B * D);
-  temb = alloc<bf16>((long long)B * D);
+  tproj = alloc<bf16>((long long)kGemvMaxB * 256);
+  h1 = alloc<bf16>((long long)kGemvMaxB * D);
+  temb = alloc<bf16>((long long)kGemvMaxB * D);
   out_buf = alloc<bf16>((long long)B * S * cfg.out_channels);
   lat_in = alloc<bf16>((long long)B * S * cfg.out_channels);
   lat_out = alloc<bf16>((long long)B * S * cfg.out_channels);
@@ -531,10 +577,32 @@ void tfx_model::prepare(int B_, int S_, int T_) {
   mQ = make_map_3d(err_, q, (long long)B * H, N, dh);
   mK = make_map_3d(err_, k, (long long)B * H, N, dh);
   mV = make_map_3d(err_, v, (long long)B * H, N, dh);
+  mK64 = make_map_3d(err_, k, (long long)B * H, N, dh, 64);
+  mV64 = make_map_3d(err_, v, (long long)B * H, N, dh, 64);
 }
 
 // The launch sequence of one FluxTransformer2DModel.forward (+ optional fused Euler update).
-void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_noise_pred) {
+// temb = time_text_embed(timestep, guidance, pooled) (transformer_flux.py:1088-1098, embeddings.py:1327-1339) for `rows`
+// (<= 8) independent rows, then every adaLN `linear(silu(temb))` in one pass over the [mod_rows, D] matrix.
+void tfx_model::enqueue_modulation(const LaunchCtx& c, const bf16* t_rows, const float* g_rows, const bf16* pooled_rows, int rows,
+                                   bf16* mod_out) {
+  timestep_embed_kernel<<<rows, 128, 0, c.stream>>>(t_rows, 0, rows, tproj);
+  ++*c.counter;
+  launch_gemv(c, tproj, rows, 256, W("t_embed.l1.w").ptr, W("t_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
+  launch_gemv(c, h1, rows, D, W("t_embed.l2.w").ptr, W("t_embed.l2.b").ptr, D, temb, 0);
+  if (cfg.guidance_embeds) {
+    timestep_embed_kernel<<<rows, 128, 0, c.stream>>>(g_rows, 1, rows, tproj);
+    ++*c.counter;
+    launch_gemv(c, tproj, rows, 256, W("g_embed.l1.w").ptr, W("g_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
+    launch_gemv(c, h1, rows, D, W("g_embed.l2.w").ptr, W("g_embed.l2.b").ptr, D, temb, GEMV_ADD_TO_OUT);
+  }
+  launch_gemv(c, pooled_rows, rows, cfg.pooled_projection_dim, W("p_embed.l1.w").ptr, W("p_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
+  launch_gemv(c, h1, rows, D, W("p_embed.l2.w").ptr, W("p_embed.l2.b").ptr, D, temb, GEMV_ADD_TO_OUT);
+  CUDA_TRY(cudaGetLastError());
+  launch_gemv(c, temb, rows, D, W("mod.w").ptr, W("mod.b").ptr, mod_rows, mod_out, GEMV_PRE_SILU);
+}
+
+void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_noise_pred, bool scheduled) {
   const long long rt = (long long)B * T, ri = (long long)B * S;
   const int L = cfg.num_layers, Ls = cfg.num_single_layers;
   char nm[96];
@@ -554,24 +622,9 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     CUDA_TRY(cudaGetLastError());
     ++*c.counter;
   }
-  // --- temb = time_text_embed(timestep, guidance, pooled) (transformer_flux.py:1088-1098, embeddings.py:1327-1339)
-  {
-    timestep_embed_kernel<<<B, 128, 0, c.stream>>>(t_in, 0, B, tproj);
-    ++*c.counter;
-    launch_gemv(c, tproj, B, 256, W("t_embed.l1.w").ptr, W("t_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
-    launch_gemv(c, h1, B, D, W("t_embed.l2.w").ptr, W("t_embed.l2.b").ptr, D, temb, 0);
-    if (cfg.guidance_embeds) {
-      timestep_embed_kernel<<<B, 128, 0, c.stream>>>(g_in, 1, B, tproj);
-      ++*c.counter;
-      launch_gemv(c, tproj, B, 256, W("g_embed.l1.w").ptr, W("g_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
-      launch_gemv(c, h1, B, D, W("g_embed.l2.w").ptr, W("g_embed.l2.b").ptr, D, temb, GEMV_ADD_TO_OUT);
-    }
-    launch_gemv(c, pooled_in, B, cfg.pooled_projection_dim, W("p_embed.l1.w").ptr, W("p_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
-    launch_gemv(c, h1, B, D, W("p_embed.l2.w").ptr, W("p_embed.l2.b").ptr, D, temb, GEMV_ADD_TO_OUT);
-    CUDA_TRY(cudaGetLastError());
-  }
-  // --- every adaLN `linear(silu(temb))` of the step in one pass over the [mod_rows, D] matrix
-  launch_gemv(c, temb, B, D, W("mod.w").ptr, W("mod.b").ptr, mod_rows, mod, GEMV_PRE_SILU);
+  // --- temb + every adaLN `linear(silu(temb))` of the step; with a schedule set they were computed for all steps at
+  //     once (tfx_set_schedule) and this step's rows were copied into `mod` before the launch
+  if (!scheduled) enqueue_modulation(c, t_in, g_in, pooled_in, B, mod);
 
   auto base_params = [&](int Nn, int Kk) {
     GemmParams p;
@@ -624,7 +677,8 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
       }
       gemm(c, 256, A_NBUF, name("d%d.qkv_c", i, ".w"), name("d%d.qkv_x", i, ".w"), p);
     }
-    launch_attention(c, dh, attn_q_tiles, mQ, mK, mV, ap);
+    if (attn_variant == 2) launch_attention2(c, dh, mQ, mK64, mV64, ap);
+    else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, D);
       p.mode0 = EPI_GATE_RES;
@@ -676,7 +730,8 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
       const std::string wn = name("s%d.qkvmlp", j, ".w");
       gemm(c, 256, A_NBUF, wn, wn, p);
     }
-    launch_attention(c, dh, attn_q_tiles, mQ, mK, mV, ap);
+    if (attn_variant == 2) launch_attention2(c, dh, mQ, mK64, mV64, ap);
+    else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, 5 * D);
       p.mode0 = EPI_GATE_RES;
@@ -710,12 +765,12 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
   }
 }
 
-void tfx_model::run(bool fused_euler, bool want_noise_pred) {
+void tfx_model::run(bool fused_euler, bool want_noise_pred, bool scheduled) {
   LaunchCtx c{stream, device, &launches, err_};
-  cudaGraphExec_t& exec = fused_euler ? graph_step : graph_fwd;
+  const int gi = (fused_euler ? 2 : 0) + (scheduled ? 1 : 0);
   if (profile) {
     c.prof = &prof;
-    enqueue_forward(c, fused_euler, want_noise_pred);
+    enqueue_forward(c, fused_euler, want_noise_pred, scheduled);
     double us[KF_COUNT];
     long long n[KF_COUNT];
     prof.collect(us, n);
@@ -723,28 +778,29 @@ void tfx_model::run(bool fused_euler, bool want_noise_pred) {
     return;
   }
   if (!use_graph) {
-    enqueue_forward(c, fused_euler, want_noise_pred);
+    enqueue_forward(c, fused_euler, want_noise_pred, scheduled);
     return;
   }
-  if (!exec) {
+  if (!graphs[gi]) {
     long long scratch = 0;
     LaunchCtx cc{stream, device, &scratch, err_};
     cudaGraph_t graph = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
     try {
-      enqueue_forward(cc, fused_euler, true);
+      enqueue_forward(cc, fused_euler, true, scheduled);
     } catch (...) {
       cudaStreamEndCapture(stream, &graph);
       if (graph) cudaGraphDestroy(graph);
       throw;
     }
     CUDA_TRY(cudaStreamEndCapture(stream, &graph));
-    CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+    CUDA_TRY(cudaGraphInstantiate(&graphs[gi], graph, 0));
     cudaGraphDestroy(graph);
+    graph_kernels[gi] = scratch;
     graph_nodes = scratch;
   }
-  CUDA_TRY(cudaGraphLaunch(exec, stream));
-  launches += graph_nodes;
+  CUDA_TRY(cudaGraphLaunch(graphs[gi], stream));
+  launches += graph_kernels[gi];
 }
 
 // ==================================================================================================== C ABI
@@ -825,6 +881,12 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
   } else if (k == "attn_q_tiles") {
     REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
     h->attn_q_tiles = (int)value;
+  } else if (k == "attn_variant") {
+    REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "attn_variant must be 1 or 2");
+    h->attn_variant = (int)value;
+  } else if (k == "attn_emu") {
+    REQUIRE(value == 0 || (value >= 2 && value <= 4), TFX_ERR_INVALID, "attn_emu must be 0, 2, 3 or 4");
+    h->attn_emu = (int)value;
   } else if (k == "use_graph") {
     h->use_graph = value != 0;
   } else if (k == "profile") {
@@ -833,8 +895,7 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
   } else {
     REQUIRE(false, TFX_ERR_INVALID, "unknown option '%s'", key);
   }
-  if (h->graph_fwd) { cudaGraphExecDestroy(h->graph_fwd); h->graph_fwd = nullptr; }
-  if (h->graph_step) { cudaGraphExecDestroy(h->graph_step); h->graph_step = nullptr; }
+  h->drop_graphs();
   API_END
 }
 
@@ -919,17 +980,19 @@ int tfx_prepare(tfx_handle h, int32_t B, int32_t S, int32_t T) {
 }
 
 static void stage_common(tfx_model* h, std::string* err_, const void* enc, const void* pooled, const void* t, const void* g,
-                         const void* img_ids, const void* txt_ids, cudaStream_t user) {
+                         const void* img_ids, const void* txt_ids, cudaStream_t user, bool scheduled = false) {
   REQUIRE(h->B > 0, TFX_ERR_STATE, "tfx_prepare has not been called");
-  REQUIRE(enc && pooled && t && img_ids && txt_ids, TFX_ERR_INVALID, "null input pointer");
-  REQUIRE(!h->cfg.guidance_embeds || g, TFX_ERR_INVALID, "guidance is required when guidance_embeds is set");
+  REQUIRE(enc && img_ids && txt_ids && (scheduled || (pooled && t)), TFX_ERR_INVALID, "null input pointer");
+  REQUIRE(scheduled || !h->cfg.guidance_embeds || g, TFX_ERR_INVALID, "guidance is required when guidance_embeds is set");
   CUDA_TRY(cudaEventRecord(h->ev_in, user));
   CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in, 0));
   cudaStream_t s = h->stream;
   CUDA_TRY(cudaMemcpyAsync(h->enc_in, enc, (size_t)h->B * h->T * h->cfg.joint_attention_dim * 2, cudaMemcpyDeviceToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(h->pooled_in, pooled, (size_t)h->B * h->cfg.pooled_projection_dim * 2, cudaMemcpyDeviceToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(h->t_in, t, (size_t)h->B * 2, cudaMemcpyDeviceToDevice, s));
-  if (h->cfg.guidance_embeds) CUDA_TRY(cudaMemcpyAsync(h->g_in, g, (size_t)h->B * 4, cudaMemcpyDeviceToDevice, s));
+  if (!scheduled) {
+    CUDA_TRY(cudaMemcpyAsync(h->pooled_in, pooled, (size_t)h->B * h->cfg.pooled_projection_dim * 2, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->t_in, t, (size_t)h->B * 2, cudaMemcpyDeviceToDevice, s));
+    if (h->cfg.guidance_embeds) CUDA_TRY(cudaMemcpyAsync(h->g_in, g, (size_t)h->B * 4, cudaMemcpyDeviceToDevice, s));
+  }
   CUDA_TRY(cudaMemcpyAsync(h->ids_img, img_ids, (size_t)h->S * 3 * 2, cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(h->ids_txt, txt_ids, (size_t)h->T * 3 * 2, cudaMemcpyDeviceToDevice, s));
 }
@@ -948,7 +1011,7 @@ int tfx_forward(tfx_handle h, const void* hidden_states, const void* encoder_hid
   cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
   stage_common(h, err_, encoder_hidden_states, pooled, timestep_bf16, guidance_f32, img_ids, txt_ids, user);
   CUDA_TRY(cudaMemcpyAsync(h->x_in, hidden_states, (size_t)h->B * h->S * h->cfg.in_channels * 2, cudaMemcpyDeviceToDevice, h->stream));
-  h->run(false, true);
+  h->run(false, true, false);
   CUDA_TRY(cudaMemcpyAsync(out_sample, h->out_buf, (size_t)h->B * h->S * h->cfg.out_channels * 2, cudaMemcpyDeviceToDevice, h->stream));
   finish(h, err_, user);
   API_END
@@ -972,7 +1035,77 @@ int tfx_step(tfx_handle h, const void* latents_in, const void* cond, const void*
   const float dt = __bfloat162float(__float2bfloat16_rn(sigma_next - sigma));
   set_float_kernel<<<1, 1, 0, s>>>(h->dt_dev, dt);
   ++h->launches;
-  h->run(true, noise_pred_out != nullptr);
+  h->run(true, noise_pred_out != nullptr, false);
+  CUDA_TRY(cudaMemcpyAsync(latents_out, h->lat_out, rows * Cl * 2, cudaMemcpyDeviceToDevice, s));
+  if (noise_pred_out) CUDA_TRY(cudaMemcpyAsync(noise_pred_out, h->out_buf, rows * Cl * 2, cudaMemcpyDeviceToDevice, s));
+  finish(h, err_, user);
+  API_END
+}
+
+// Step-invariant work hoisted out of the loop: temb depends only on (t_i, guidance, pooled),
+// all known once set_timesteps has run, so the modulation vectors of every step are produced here with ceil(n*B/8)
+// passes over the 6.5 GB adaLN matrix instead of one pass per step.
+int tfx_set_schedule(tfx_handle h, const void* timesteps_bf16, int32_t n_steps, const void* guidance_f32, const void* pooled,
+                     void* stream) {
+  API_BEGIN(h)
+  REQUIRE(h && timesteps_bf16 && pooled && n_steps > 0, TFX_ERR_INVALID, "bad argument");
+  REQUIRE(h->B > 0, TFX_ERR_STATE, "tfx_prepare has not been called");
+  REQUIRE(!h->cfg.guidance_embeds || guidance_f32, TFX_ERR_INVALID, "guidance is required when guidance_embeds is set");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+  const int B = h->B, P = h->cfg.pooled_projection_dim;
+  const long long rows = (long long)n_steps * B;
+  if (h->sched_steps != n_steps) {
+    if (h->mod_table) cudaFree(h->mod_table);
+    if (h->sched_g) cudaFree(h->sched_g);
+    if (h->sched_pooled) cudaFree(h->sched_pooled);
+    h->mod_table = nullptr; h->sched_g = nullptr; h->sched_pooled = nullptr; h->sched_steps = 0;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->mod_table), (size_t)rows * h->mod_rows * 2));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->sched_g), (size_t)rows * 4 + 256));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->sched_pooled), (size_t)rows * P * 2 + 256));
+    h->sched_steps = n_steps;
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_in, user));
+  CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_in, 0));
+  cudaStream_t s = h->stream;
+  // row r = step * B + b uses timestep[step][b], guidance[b], pooled[b]
+  for (int st = 0; st < n_steps; ++st) {
+    if (h->cfg.guidance_embeds)
+      CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<float*>(h->sched_g) + (size_t)st * B, guidance_f32, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(h->sched_pooled + (size_t)st * B * P, pooled, (size_t)B * P * 2, cudaMemcpyDeviceToDevice, s));
+  }
+  LaunchCtx c{s, h->device, &h->launches, err_};
+  for (long long r0 = 0; r0 < rows; r0 += kGemvMaxB) {
+    const int nr = (int)((rows - r0 < kGemvMaxB) ? rows - r0 : kGemvMaxB);
+    h->enqueue_modulation(c, reinterpret_cast<const bf16*>(timesteps_bf16) + r0, reinterpret_cast<const float*>(h->sched_g) + r0,
+                          h->sched_pooled + r0 * P, nr, h->mod_table + r0 * h->mod_rows);
+  }
+  finish(h, err_, user);
+  API_END
+}
+
+int tfx_step_scheduled(tfx_handle h, int32_t step_index, const void* latents_in, const void* cond,
+                       const void* encoder_hidden_states, const void* img_ids, const void* txt_ids, float sigma, float sigma_next,
+                       void* latents_out, void* noise_pred_out, void* stream) {
+  API_BEGIN(h)
+  REQUIRE(h && latents_in && cond && latents_out, TFX_ERR_INVALID, "null argument");
+  REQUIRE(h->mod_table && step_index >= 0 && step_index < h->sched_steps, TFX_ERR_STATE,
+          "step %d outside the schedule set by tfx_set_schedule (%d steps)", step_index, h->sched_steps);
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+  stage_common(h, err_, encoder_hidden_states, nullptr, nullptr, nullptr, img_ids, txt_ids, user, true);
+  const int Cl = h->cfg.out_channels, Cc = h->cfg.in_channels - h->cfg.out_channels, Ci = h->cfg.in_channels;
+  const size_t rows = (size_t)h->B * h->S;
+  cudaStream_t s = h->stream;
+  CUDA_TRY(cudaMemcpy2DAsync(h->x_in, (size_t)Ci * 2, latents_in, (size_t)Cl * 2, (size_t)Cl * 2, rows, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpy2DAsync(h->x_in + Cl, (size_t)Ci * 2, cond, (size_t)Cc * 2, (size_t)Cc * 2, rows, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->lat_in, latents_in, rows * Cl * 2, cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->mod, h->mod_table + (size_t)step_index * h->B * h->mod_rows, (size_t)h->B * h->mod_rows * 2,
+                           cudaMemcpyDeviceToDevice, s));
+  const float dt = __bfloat162float(__float2bfloat16_rn(sigma_next - sigma));
+  set_float_kernel<<<1, 1, 0, s>>>(h->dt_dev, dt);
+  ++h->launches;
+  h->run(true, noise_pred_out != nullptr, true);
   CUDA_TRY(cudaMemcpyAsync(latents_out, h->lat_out, rows * Cl * 2, cudaMemcpyDeviceToDevice, s));
   if (noise_pred_out) CUDA_TRY(cudaMemcpyAsync(noise_pred_out, h->out_buf, rows * Cl * 2, cudaMemcpyDeviceToDevice, s));
   finish(h, err_, user);
@@ -1053,7 +1186,13 @@ int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int
     p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
     p.out = reinterpret_cast<bf16*>(out); p.ld_out = ld_out;
     LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
-    launch_attention(c, head_dim, q_tiles, mq, mk, mv, p);
+    if (q_tiles == 3) {
+      CUtensorMap mk64 = make_map_3d(err_, k, (long long)B * H, N, head_dim, 64);
+      CUtensorMap mv64 = make_map_3d(err_, v, (long long)B * H, N, head_dim, 64);
+      launch_attention2(c, head_dim, mq, mk64, mv64, p);
+    } else {
+      launch_attention(c, head_dim, q_tiles % 10, q_tiles / 10, mq, mk, mv, p);
+    }
   } catch (const Fail& f) {
     return f.code;
   }

@@ -232,26 +232,68 @@ class B200FluxTransformer(torch.nn.Module):
         return (out, pred) if return_noise_pred else out
 
     @torch.no_grad()
+    def set_schedule(self, timesteps: Tensor, guidance: Optional[Tensor], pooled_projections: Tensor, S: int, T: int) -> None:
+        """Precompute temb and every adaLN modulation vector for all steps of a schedule (they depend only on
+        (t_i, guidance, pooled)): `timesteps` is [n, B] = t/1000 in bf16, exactly what the pipeline would pass at step i."""
+        c = self.config
+        n, B = timesteps.shape
+        ts = timesteps.to(device=self._dev, dtype=torch.bfloat16).contiguous()
+        pooled = self._bf16(pooled_projections, "pooled_projections", (B, c.pooled_projection_dim))
+        g = guidance.to(device=self._dev, dtype=torch.float32).expand(B).contiguous() if c.guidance_embeds else None
+        with torch.cuda.device(self._dev):
+            self._prepare(B, S, T)
+            stream = torch.cuda.current_stream(self._dev).cuda_stream
+            _lib.check(self._lib.tfx_set_schedule(self._h, ts.data_ptr(), n, _ptr(g), pooled.data_ptr(), stream), self._h)
+
+    @torch.no_grad()
+    def step_scheduled(self, i: int, latents: Tensor, cond: Tensor, encoder_hidden_states: Tensor, img_ids: Tensor,
+                       txt_ids: Tensor, sigma: float, sigma_next: float, return_noise_pred: bool = False):
+        """`step` for step i of the schedule given to `set_schedule` (bit-identical results, no per-step adaLN pass)."""
+        c = self.config
+        B, S, _ = latents.shape
+        T = encoder_hidden_states.shape[1]
+        lat = self._bf16(latents, "latents", (B, S, c.out_channels))
+        cnd = self._bf16(cond, "cond", (B, S, c.in_channels - c.out_channels))
+        enc = self._bf16(encoder_hidden_states, "encoder_hidden_states", (B, T, c.joint_attention_dim))
+        img = self._ids(img_ids, "img_ids", S)
+        txt = self._ids(txt_ids, "txt_ids", T)
+        out = torch.empty_like(lat)
+        pred = torch.empty_like(lat) if return_noise_pred else None
+        with torch.cuda.device(self._dev):
+            if self._shape != (B, S, T):
+                raise RuntimeError("textflux_b200: step_scheduled called with a different shape than set_schedule")
+            stream = torch.cuda.current_stream(self._dev).cuda_stream
+            _lib.check(self._lib.tfx_step_scheduled(self._h, int(i), lat.data_ptr(), cnd.data_ptr(), enc.data_ptr(),
+                                                    img.data_ptr(), txt.data_ptr(), float(sigma), float(sigma_next),
+                                                    out.data_ptr(), _ptr(pred), stream), self._h)
+        return (out, pred) if return_noise_pred else out
+
+    @torch.no_grad()
     def denoise(self, latents: Tensor, cond: Tensor, prompt_embeds: Tensor, pooled_prompt_embeds: Tensor,
                 txt_ids: Tensor, img_ids: Tensor, guidance_scale: float, num_inference_steps: int,
                 scheduler: Optional["B200FlowMatchEulerScheduler"] = None,
-                callback: Optional[Callable[[int, Tensor], None]] = None) -> Tensor:
+                callback: Optional[Callable[[int, Tensor], None]] = None, precompute_modulation: bool = True) -> Tensor:
         """The whole loop of FluxFillPipeline.__call__ (pipeline_flux_fill.py:2049-2119): schedule, then one fused
         step per timestep.  Returns the final packed latents."""
         sch = scheduler or B200FlowMatchEulerScheduler()
-        S = latents.shape[1]
+        B, S = latents.shape[0], latents.shape[1]
+        T = prompt_embeds.shape[1]
         mu = calculate_shift(S, sch.config.base_image_seq_len, sch.config.max_image_seq_len, sch.config.base_shift,
                              sch.config.max_shift)
         sch.set_timesteps(sigmas=np.linspace(1.0, 1 / num_inference_steps, num_inference_steps), device=self._dev, mu=mu)
-        B = latents.shape[0]
         guidance = torch.full([1], guidance_scale, device=self._dev, dtype=torch.float32).expand(B) \
             if self.config.guidance_embeds else None
         # timestep = t.expand(B).to(latents.dtype); transformer(timestep / 1000)   (:2082,2086)
         ts = (sch.timesteps.to(self._dev)[:, None].expand(-1, B).to(latents.dtype) / 1000).contiguous()
         sig = sch.sigmas_cpu
+        if precompute_modulation:
+            self.set_schedule(ts, guidance, pooled_prompt_embeds, S, T)
         for i in range(len(sch.timesteps)):
-            latents = self.step(latents, cond, prompt_embeds, pooled_prompt_embeds, ts[i], guidance, img_ids, txt_ids,
-                                sig[i], sig[i + 1])
+            if precompute_modulation:
+                latents = self.step_scheduled(i, latents, cond, prompt_embeds, img_ids, txt_ids, sig[i], sig[i + 1])
+            else:
+                latents = self.step(latents, cond, prompt_embeds, pooled_prompt_embeds, ts[i], guidance, img_ids, txt_ids,
+                                    sig[i], sig[i + 1])
             if callback is not None:
                 callback(i, latents)
         return latents

@@ -33,6 +33,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--json", default=None)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="")
     args = ap.parse_args()
     lib = _lib.load()
     st = torch.cuda.current_stream().cuda_stream
@@ -44,6 +45,8 @@ def main():
               (8192, 8192, 8192, "square 8192")]
     if args.quick:
         shapes = shapes[:4]
+    if args.only and args.only != "gemm":
+        shapes = []
     for M, N, K, name in shapes:
         A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         W = (torch.randn(N, K, device="cuda") * 0.02).to(torch.bfloat16)
@@ -76,7 +79,7 @@ def main():
         print(row, flush=True)
         res.append(row)
         del A, W, out
-    for (T, S) in [(512, 2048), (512, 4608), (512, 8192)]:
+    for (T, S) in ([] if args.only not in ("", "attention") else [(512, 2048), (512, 4608), (512, 8192)]):
         H, dh, N = 24, 128, T + S
         q = torch.randn(1, H, N, dh, device="cuda").to(torch.bfloat16)
         k = torch.randn(1, H, N, dh, device="cuda").to(torch.bfloat16)
@@ -84,7 +87,7 @@ def main():
         out = torch.empty(N, H * dh, device="cuda", dtype=torch.bfloat16)
         row = {"kernel": "attention", "N": N, "H": H, "dh": dh}
         fl = 4.0 * N * N * H * dh
-        for qt in (1, 2):
+        for qt in (2, 3):
             def f():
                 _lib.check(lib.tfx_op_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), H * dh, 1, H, T, S, dh, qt, st))
             ms = timeit(f, flush=flush)
