@@ -49,7 +49,7 @@ int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
 void tfx_destroy(tfx_handle h);
 /* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
 const char* tfx_last_error(tfx_handle h);
-/* "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1|2), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "profile" (0|1: eager launches, one CUDA-event
+/* "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1|2|3), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "profile" (0|1: eager launches, one CUDA-event
  * pair per kernel, summed per family; resets the sums) */
 int tfx_set_option(tfx_handle h, const char* key, int64_t value);
 /* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step;
@@ -104,7 +104,8 @@ int tfx_step_scheduled(tfx_handle h, int32_t step_index, const void* latents_in,
 int tfx_op_linear(const void* A, int64_t lda, const void* W, const void* bias, void* out, int64_t ldo, int32_t M,
                   int32_t N, int32_t K, int32_t mode, const void* gate, const void* res, int32_t cta_group, void* stream);
 /* q,k,v [B,H,N,dh] -> out rows in the engine's [B*T text rows ; B*S image rows] order, row stride ld_out;
- * q_tiles = 3: QK-ahead schedule (default in the engine); else v1 schedule with q_tiles = tiles + 10 * emu
+ * q_tiles = 3 | 4: QK-ahead schedule (2 query tiles x 64-key tiles | 1 query tile x 128-key tiles); else v1 schedule
+ * with q_tiles = tiles + 10 * emu
  * (emu = exponentials per 8 evaluated by the FMA-pipe polynomial: 0, 2, 3, 4) */
 int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int64_t ld_out, int32_t B, int32_t H,
                      int32_t T, int32_t S, int32_t head_dim, int32_t q_tiles, void* stream);

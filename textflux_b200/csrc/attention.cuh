@@ -316,65 +316,73 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Version 2 of the schedule ("QK-ahead").  In the kernel above a query tile's chain is strictly
+// Version 2 of the schedule ("QK-ahead"), templated on query tiles per CTA (kQT) and keys per tile (kKV).  In the kernel above a query tile's chain is strictly
 //   softmax(j) -> PV(j), QK(j+1) -> softmax(j+1): softmax warps and the tensor pipe wait on each other (ncu: 31 % of
 // warp samples sit in the wait for S, tensor pipe 46 % busy, profiles/r1d).  Here KV tiles are 64 keys, so the
 // 512 TMEM columns hold TWO score buffers per query tile (2 q-tiles x 2 x 64) next to the two O accumulators
 // (2 x 128), and the issuer runs QK two tiles ahead: S(j+1) is already in TMEM when softmax(j) finishes, the softmax
 // warpgroups run back to back and the MMAs (PV(j), QK(j+2)) execute in their shadow.
-template <int kHeadDim>
+template <int kHeadDim, int kQT, int kKV>
 struct Attn2Cfg {
   static constexpr int kHalves = kHeadDim / 64;
   static constexpr int kQBytes = 128 * kHeadDim * 2;   // one 128-row query tile
-  static constexpr int kKvRows = 64;
+  static constexpr int kKvRows = kKV;
   static constexpr int kKvBytes = kKvRows * kHeadDim * 2;  // one K (or V) tile
-  static constexpr int kStages = 4;
-  static constexpr int kThreads = 64 + 256;
-  static constexpr int kSmemBytes = 2 * kQBytes + kStages * 2 * kKvBytes + 1024 + 256;
-  static constexpr int kOCol = 256;  // S[q][b] at (q*2+b)*64, O_q at 256 + q*128
+  // K runs two tiles ahead of V (QK(j+2) is issued next to PV(j)), so the rings are separate: 4 K stages, and as many
+  // V stages as the 227 KB allow
+  static constexpr int kKStages = 4;
+  static constexpr int kVStages = (kQT * kQBytes + 8 * kKvBytes <= 200 * 1024) ? 4 : 2;
+  static constexpr int kThreads = 64 + 128 * kQT;
+  static constexpr int kSmemBytes = kQT * kQBytes + (kKStages + kVStages) * kKvBytes + 1024 + 256;
+  static constexpr int kOCol = kQT * 2 * kKV;  // S[q][b] at (q*2+b)*kKV, O_q at kOCol + q*128
+  static_assert(kQT * 2 * kKV + kQT * 128 <= 512, "TMEM budget");
 };
 
-template <int kHeadDim>
-__global__ void __launch_bounds__(Attn2Cfg<kHeadDim>::kThreads, 1)
+template <int kHeadDim, int kQT, int kKV>
+__global__ void __launch_bounds__(Attn2Cfg<kHeadDim, kQT, kKV>::kThreads, 1)
 attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
-  using Cfg = Attn2Cfg<kHeadDim>;
+  using Cfg = Attn2Cfg<kHeadDim, kQT, kKV>;
   constexpr int kHalves = Cfg::kHalves;
-  constexpr int kStages = Cfg::kStages;
+  constexpr int kKS = Cfg::kKStages, kVS = Cfg::kVStages;
   constexpr int kQHalfBytes = 128 * 128;  // 128 rows x 128 B
-  constexpr int kKvHalfBytes = 64 * 128;  // 64 rows x 128 B
+  constexpr int kKvHalfBytes = kKV * 128;  // kKV rows x 128 B
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                           // [2][kHalves][128][64]
-  uint8_t* sK = sQ + 2 * Cfg::kQBytes;          // [stages][kHalves][64][64]
-  uint8_t* sV = sK + kStages * Cfg::kKvBytes;   // [stages][kHalves][64 kv][64 dh]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages * Cfg::kKvBytes);
+  uint8_t* sQ = smem;                           // [kQT][kHalves][128][64]
+  uint8_t* sK = sQ + kQT * Cfg::kQBytes;        // [stages][kHalves][kKV][64]
+  uint8_t* sV = sK + kKS * Cfg::kKvBytes;       // [stages][kHalves][kKV kv][64 dh]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kVS * Cfg::kKvBytes);
   uint64_t* q_full = bars;                 // [1]
-  uint64_t* k_full = q_full + 1;           // [stages]
-  uint64_t* v_full = k_full + kStages;     // [stages]
-  uint64_t* kv_empty = v_full + kStages;   // [stages]
-  uint64_t* s_full = kv_empty + kStages;   // [2 q][2 buffers]
+  uint64_t* k_full = q_full + 1;           // [kKS]
+  uint64_t* k_empty = k_full + kKS;        // [kKS]
+  uint64_t* v_full = k_empty + kKS;        // [kVS]
+  uint64_t* v_empty = v_full + kVS;        // [kVS]
+  uint64_t* s_full = v_empty + kVS;        // [2 q][2 buffers]
   uint64_t* p_full = s_full + 4;           // [2]
   uint64_t* pv_done = p_full + 2;          // [2]
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256;
+  const int q0 = blockIdx.x * (128 * kQT);
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int bh = b * p.H + head;
-  const int n_kv = (p.N + 63) / 64;
+  const int n_kv = (p.N + kKV - 1) / kKV;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmQ);
     prefetch_tensormap(&tmK);
     prefetch_tensormap(&tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kKS; ++i) {
       mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < kVS; ++i) {
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
     for (int i = 0; i < 2; ++i) {
@@ -394,31 +402,36 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    mbar_arrive_expect_tx(q_full, 2 * Cfg::kQBytes);
-    for (int q = 0; q < 2; ++q)
+    mbar_arrive_expect_tx(q_full, kQT * Cfg::kQBytes);
+    for (int q = 0; q < kQT; ++q)
       for (int h = 0; h < kHalves; ++h)
         tma_load_3d(&tmQ, q_full, sQ + q * Cfg::kQBytes + h * kQHalfBytes, h * 64, q0 + q * 128, bh, kEvictFirst);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&kv_empty[stage], phase ^ 1);
-      mbar_arrive_expect_tx(&k_full[stage], Cfg::kKvBytes);
-      for (int h = 0; h < kHalves; ++h)
-        tma_load_3d(&tmK, &k_full[stage], sK + stage * Cfg::kKvBytes + h * kKvHalfBytes, h * 64, j * 64, bh, kEvictLast);
-      mbar_arrive_expect_tx(&v_full[stage], Cfg::kKvBytes);
-      for (int h = 0; h < kHalves; ++h)
-        tma_load_3d(&tmV, &v_full[stage], sV + stage * Cfg::kKvBytes + h * kKvHalfBytes, h * 64, j * 64, bh, kEvictLast);
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    // K tiles run two ahead of V tiles, like their consumers
+    for (int t = 0; t < n_kv + 2; ++t) {
+      if (t < n_kv) {
+        const int st = t % kKS;
+        mbar_wait(&k_empty[st], ((t / kKS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], Cfg::kKvBytes);
+        for (int h = 0; h < kHalves; ++h)
+          tma_load_3d(&tmK, &k_full[st], sK + st * Cfg::kKvBytes + h * kKvHalfBytes, h * 64, t * kKV, bh, kEvictLast);
+      }
+      if (t >= 2) {
+        const int j = t - 2, st = j % kVS;
+        mbar_wait(&v_empty[st], ((j / kVS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], Cfg::kKvBytes);
+        for (int h = 0; h < kHalves; ++h)
+          tma_load_3d(&tmV, &v_full[st], sV + st * Cfg::kKvBytes + h * kKvHalfBytes, h * 64, j * kKV, bh, kEvictLast);
+      }
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 64, 0, 0);
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, kKV, 0, 0);
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, kHeadDim, 0, 1);
     auto issue_qk = [&](int q, int j) {
-      const int stage = j % kStages;
+      const int stage = j % kKS;
       const uint32_t a0 = smem_u32(sQ + q * Cfg::kQBytes);
       const uint32_t b0 = smem_u32(sK + stage * Cfg::kKvBytes);
-      const uint32_t d = tmem_base + uint32_t((q * 2 + (j & 1)) * 64);
+      const uint32_t d = tmem_base + uint32_t((q * 2 + (j & 1)) * kKV);
 #pragma unroll
       for (int kk = 0; kk < kHeadDim / 16; ++kk) {
         umma_ss<1>(d, make_smem_desc(a0 + uint32_t((kk / 4) * kQHalfBytes + (kk % 4) * 32), 16, 1024, kLayoutSW128),
@@ -427,11 +440,11 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       umma_commit(&s_full[q * 2 + (j & 1)]);
     };
     auto issue_pv = [&](int q, int j) {
-      const int stage = j % kStages;
+      const int stage = j % kVS;
       const uint32_t v0 = smem_u32(sV + stage * Cfg::kKvBytes);
-      const uint32_t pcol = tmem_base + uint32_t((q * 2 + (j & 1)) * 64);
+      const uint32_t pcol = tmem_base + uint32_t((q * 2 + (j & 1)) * kKV);
 #pragma unroll
-      for (int kk = 0; kk < 64 / 16; ++kk) {
+      for (int kk = 0; kk < kKV / 16; ++kk) {
         umma_ts(tmem_base + uint32_t(Cfg::kOCol + q * 128), pcol + uint32_t(kk * 8),
                 make_smem_desc(v0 + kk * 2048, kKvHalfBytes, 1024, kLayoutSW128), idesc_pv, (j | kk) != 0);
       }
@@ -439,24 +452,24 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     };
     mbar_wait(q_full, 0);
     for (int j = 0; j < 2 && j < n_kv; ++j) {  // run two KV tiles ahead
-      mbar_wait(&k_full[j % kStages], 0);
+      mbar_wait(&k_full[j % kKS], 0);
       tc_fence_after();
-      issue_qk(0, j);
-      issue_qk(1, j);
+      for (int q = 0; q < kQT; ++q) issue_qk(q, j);
+      umma_commit(&k_empty[j % kKS]);
     }
     for (int j = 0; j < n_kv; ++j) {
-      const int stage = j % kStages;
-      mbar_wait(&v_full[stage], (j / kStages) & 1);
-      for (int q = 0; q < 2; ++q) {
+      mbar_wait(&v_full[j % kVS], (j / kVS) & 1);
+      for (int q = 0; q < kQT; ++q) {
         mbar_wait(&p_full[q], j & 1);
         tc_fence_after();
         issue_pv(q, j);
         if (j + 2 < n_kv) {
-          if (q == 0) { mbar_wait(&k_full[(j + 2) % kStages], ((j + 2) / kStages) & 1); tc_fence_after(); }
+          if (q == 0) { mbar_wait(&k_full[(j + 2) % kKS], ((j + 2) / kKS) & 1); tc_fence_after(); }
           issue_qk(q, j + 2);  // overwrites S[q][j&1] = P(q,j): ordered behind PV(q,j) by the in-order tensor pipe
+          if (q == kQT - 1) umma_commit(&k_empty[(j + 2) % kKS]);
         }
       }
-      umma_commit(&kv_empty[stage]);
+      umma_commit(&v_empty[j % kVS]);
     }
   } else if (warp >= 2) {
     // ===================== softmax warpgroups: one thread per query row =====================
@@ -469,46 +482,51 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     const float kRescaleThreshold = 8.0f;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
-      const int valid = p.N - j * 64;
-      const uint32_t t_s = t_lane + uint32_t((q * 2 + (j & 1)) * 64);
+      const int valid = p.N - j * kKV;
+      const uint32_t t_s = t_lane + uint32_t((q * 2 + (j & 1)) * kKV);
       mbar_wait(&s_full[q * 2 + (j & 1)], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t sr[2][32];
-      tmem_ld32(t_s, sr[0]);
-      tmem_ld32(t_s + 32, sr[1]);
-      tmem_ld_wait();
-      if (valid < 64) {
+      constexpr int kCh = kKV / 32;
+      uint32_t sr[kCh][32];
 #pragma unroll
-        for (int cch = 0; cch < 2; ++cch)
+      for (int cch = 0; cch < kCh; ++cch) tmem_ld32(t_s + cch * 32, sr[cch]);
+      tmem_ld_wait();
+      if (valid < kKV) {
+#pragma unroll
+        for (int cch = 0; cch < kCh; ++cch)
 #pragma unroll
           for (int i = 0; i < 32; ++i)
             if (cch * 32 + i >= valid) sr[cch][i] = 0xff800000u;
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
+      float mxa[kCh];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
-        mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
-      }
-      const float mx = fmaxf(mx0, mx1);
+      for (int cch = 0; cch < kCh; ++cch) mxa[cch] = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+#pragma unroll
+        for (int cch = 0; cch < kCh; ++cch) mxa[cch] = fmaxf(mxa[cch], __uint_as_float(sr[cch][i]));
+      float mx = mxa[0];
+#pragma unroll
+      for (int cch = 1; cch < kCh; ++cch) mx = fmaxf(mx, mxa[cch]);
       const bool need = (mx - m) * c > kRescaleThreshold;
       const float m_new = need ? mx : m;
       const float alpha = need ? ex2((m - m_new) * c) : 1.0f;
       const float mc = m_new * c;
       float sum0 = 0.f, sum1 = 0.f;
-      uint32_t pk[32];
+      uint32_t pk[kCh / 2][32];
 #pragma unroll
-      for (int cch = 0; cch < 2; ++cch) {
+      for (int cch = 0; cch < kCh; ++cch) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const float p0 = ex2(fmaf(__uint_as_float(sr[cch][i]), c, -mc));
           const float p1 = ex2(fmaf(__uint_as_float(sr[cch][i + 1]), c, -mc));
           sum0 += p0;
           sum1 += p1;
-          pk[cch * 16 + (i >> 1)] = pack_bf16(p0, p1);
+          pk[cch >> 1][(cch & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
         }
       }
-      tmem_st32(t_s, pk);
+#pragma unroll
+      for (int h2 = 0; h2 < kCh / 2; ++h2) tmem_st32(t_s + h2 * 32, pk[h2]);
       l = l * alpha + (sum0 + sum1);
       m = m_new;
       tmem_st_wait();

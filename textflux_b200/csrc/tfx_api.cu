@@ -175,8 +175,10 @@ void configure_kernels(std::string* err_) {
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<128>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<64>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<128, 2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<128, 2, 64>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<64, 2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<64, 2, 64>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<128, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<128, 1, 128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<64, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<64, 1, 128>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 1>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 2>::kSmemBytes));
@@ -357,17 +359,22 @@ void launch_attention(const LaunchCtx& c, int head_dim, int q_tiles, int emu, co
   ++*c.counter;
 }
 
-// "QK-ahead" schedule: 256 query rows per CTA, 64-key tiles; tk/tv must be descriptors with 64-row boxes
-void launch_attention2(const LaunchCtx& c, int head_dim, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                       const AttnParams& p) {
+// "QK-ahead" schedule.  mode 2: 2 query tiles per CTA, 64-key tiles (tk/tv: 64-row boxes); mode 3: 1 query tile per
+// CTA, 128-key tiles (tk/tv: 128-row boxes).
+void launch_attention2(const LaunchCtx& c, int head_dim, int mode, const CUtensorMap& tq, const CUtensorMap& tk,
+                       const CUtensorMap& tv, const AttnParams& p) {
   std::string* err_ = c.err_;
   REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
   ProfScope ps(c, KF_ATTN);
-  dim3 grid((p.N + 255) / 256, p.H, p.B);
-  if (head_dim == 128)
-    attention2_tcgen05_kernel<128><<<grid, Attn2Cfg<128>::kThreads, Attn2Cfg<128>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
-  else
-    attention2_tcgen05_kernel<64><<<grid, Attn2Cfg<64>::kThreads, Attn2Cfg<64>::kSmemBytes, c.stream>>>(tq, tk, tv, p);
+#define TFX_ATTN2(DH, QT, KV) \
+  attention2_tcgen05_kernel<DH, QT, KV><<<dim3((p.N + 128 * QT - 1) / (128 * QT), p.H, p.B), Attn2Cfg<DH, QT, KV>::kThreads, \
+                                          Attn2Cfg<DH, QT, KV>::kSmemBytes, c.stream>>>(tq, tk, tv, p)
+  if (mode == 3) {
+    if (head_dim == 128) TFX_ATTN2(128, 1, 128); else TFX_ATTN2(64, 1, 128);
+  } else {
+    if (head_dim == 128) TFX_ATTN2(128, 2, 64); else TFX_ATTN2(64, 2, 64);
+  }
+#undef TFX_ATTN2
   CUDA_TRY(cudaGetLastError());
   ++*c.counter;
 }
@@ -677,7 +684,8 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
       }
       gemm(c, 256, A_NBUF, name("d%d.qkv_c", i, ".w"), name("d%d.qkv_x", i, ".w"), p);
     }
-    if (attn_variant == 2) launch_attention2(c, dh, mQ, mK64, mV64, ap);
+    if (attn_variant == 2) launch_attention2(c, dh, 2, mQ, mK64, mV64, ap);
+    else if (attn_variant == 3) launch_attention2(c, dh, 3, mQ, mK, mV, ap);
     else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, D);
@@ -730,7 +738,8 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
       const std::string wn = name("s%d.qkvmlp", j, ".w");
       gemm(c, 256, A_NBUF, wn, wn, p);
     }
-    if (attn_variant == 2) launch_attention2(c, dh, mQ, mK64, mV64, ap);
+    if (attn_variant == 2) launch_attention2(c, dh, 2, mQ, mK64, mV64, ap);
+    else if (attn_variant == 3) launch_attention2(c, dh, 3, mQ, mK, mV, ap);
     else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, 5 * D);
@@ -882,7 +891,7 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
     REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
     h->attn_q_tiles = (int)value;
   } else if (k == "attn_variant") {
-    REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "attn_variant must be 1 or 2");
+    REQUIRE(value >= 1 && value <= 3, TFX_ERR_INVALID, "attn_variant must be 1, 2 or 3");
     h->attn_variant = (int)value;
   } else if (k == "attn_emu") {
     REQUIRE(value == 0 || (value >= 2 && value <= 4), TFX_ERR_INVALID, "attn_emu must be 0, 2, 3 or 4");
@@ -1189,7 +1198,9 @@ int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int
     if (q_tiles == 3) {
       CUtensorMap mk64 = make_map_3d(err_, k, (long long)B * H, N, head_dim, 64);
       CUtensorMap mv64 = make_map_3d(err_, v, (long long)B * H, N, head_dim, 64);
-      launch_attention2(c, head_dim, mq, mk64, mv64, p);
+      launch_attention2(c, head_dim, 2, mq, mk64, mv64, p);
+    } else if (q_tiles == 4) {
+      launch_attention2(c, head_dim, 3, mq, mk, mv, p);
     } else {
       launch_attention(c, head_dim, q_tiles % 10, q_tiles / 10, mq, mk, mv, p);
     }
