@@ -81,6 +81,14 @@ int tfx_forward(tfx_handle h, const void* hidden_states, const void* encoder_hid
 int tfx_euler_step(const void* model_output, const void* sample, void* prev_sample, int64_t n, float sigma,
                    float sigma_next, void* stream);
 
+/* replaces StochasticRFOvershotDiscreteScheduler.step, the TextFlux default sampler (demo.py:15, scripts/batch_eval.sh)
+ * in its attn_map = None form (schedulers/scheduling_stochastic_rf_discrete_overshot.py:300-366):
+ *   x_o = fp32(sample) + bf16(bf16(t_o - t) * (-v));  prev = bf16(x_o * a + noise * b);  x1 = fp32(sample) - bf16(bf16(sigma) * v)
+ * The host passes the scalars (t_o - t, a, b, sigma) and the fp32 noise drawn by torch's generator exactly where the
+ * reference draws it; predicted_x1_f32 may be NULL. */
+int tfx_overshoot_step(const void* model_output, const void* sample, const void* noise_f32, void* prev_sample,
+                       void* predicted_x1_f32, int64_t n, float t_overshoot_minus_t, float a, float b, float sigma, void* stream);
+
 /* One whole sampling step = loop body of pipeline_flux_fill.py:2082-2098 in one call: cat(latents, cond) -> forward
  * -> Euler update fused into the last GEMM's store.  latents_in/out [B,S,out_channels] (may alias),
  * cond [B,S,in_channels-out_channels], noise_pred_out optional (NULL to skip). */

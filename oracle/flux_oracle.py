@@ -403,6 +403,36 @@ def euler_step(model_output: Tensor, sigma: Tensor, sigma_next: Tensor, sample: 
     return prev.to(model_output.dtype)
 
 
+def overshoot_set_timesteps(num_inference_steps: int, image_seq_len: int, num_train_timesteps: int = 1000) -> Tuple[Tensor, Tensor]:
+    """StochasticRFOvershotDiscreteScheduler.set_timesteps with the pipeline's float64 `sigmas=np.linspace(1, 1/n, n)`
+    (scheduling_stochastic_rf_discrete_overshot.py:183-222): unlike the Euler scheduler the shift runs in float64."""
+    sig = np.linspace(1.0, 1 / num_inference_steps, num_inference_steps)
+    mu = calculate_shift(image_seq_len)
+    sig = math.exp(mu) / (math.exp(mu) + (1 / sig - 1) ** 1.0)
+    sigmas = torch.from_numpy(sig).to(dtype=torch.float32)
+    timesteps = sigmas * num_train_timesteps
+    return torch.cat([sigmas, torch.zeros(1)]), timesteps
+
+
+def overshoot_step(model_output: Tensor, sigma: Tensor, sigma_next: Tensor, sample: Tensor, noise: Tensor, c: float = 2.0):
+    """StochasticRFOvershotDiscreteScheduler.step, attn_map=None branch, overshot_func(t, dt) = t + dt, c = 2.0 as TextFlux
+    configures it (scheduling_stochastic_rf_discrete_overshot.py:300-366; run_inference.py:84-88).  `noise` is the
+    randn_tensor draw of :351-355 (fp32, sample's shape).  Returns (prev_sample, predicted_x1)."""
+    sample = sample.to(torch.float32)
+    t = 1 - sigma
+    step_size = sigma - sigma_next
+    t_next = min(t + step_size, 1)
+    step_size_overshoot = step_size * c
+    t_overshoot = min(t_next + step_size_overshoot, 1)
+    sample_overshoot = sample + (t_overshoot - t) * (-model_output)
+    a = t_next / t_overshoot
+    b = ((1 - t_next) ** 2 - (a - t_next) ** 2) ** (0.5)
+    prev_sample = sample_overshoot * a + noise * b
+    prev_sample = prev_sample.to(model_output.dtype)
+    predicted_x1 = sample - sigma * model_output
+    return prev_sample, predicted_x1
+
+
 def pack_latents(latents: Tensor) -> Tensor:
     """pipeline_flux_fill.py:1743-1748."""
     B, C, h, w = latents.shape

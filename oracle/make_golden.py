@@ -134,6 +134,33 @@ def real_dim_blocks():
                 sample=out, taps=keep)
 
 
+@torch.no_grad()
+def overshoot_steps():
+    """The TextFlux default sampler (demo.py:15, scripts/batch_eval.sh): 6 steps of the real
+    StochasticRFOvershotDiscreteScheduler on seeded bf16 tensors, c = 2.0, overshot_func(t, dt) = t + dt."""
+    import numpy as np
+    from .ref_loader import import_reference
+    d = import_reference()
+    from diffusers.schedulers.scheduling_stochastic_rf_discrete_overshot import StochasticRFOvershotDiscreteScheduler
+    sch = StochasticRFOvershotDiscreteScheduler(use_dynamic_shifting=True, base_shift=0.5, max_shift=1.15)
+    sch.set_c(2.0)
+    sch.set_overshot_func(lambda t, dt: t + dt)
+    n, S = 6, 96
+    mu = fo.calculate_shift(S)
+    sch.set_timesteps(sigmas=np.linspace(1.0, 1 / n, n), mu=mu)
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn(2, S, 64, generator=g).to(torch.bfloat16)
+    vs = [torch.randn(2, S, 64, generator=g).to(torch.bfloat16) for _ in range(n)]
+    gen = torch.Generator().manual_seed(777)
+    prevs, x1s = [], []
+    for i, t in enumerate(sch.timesteps):
+        x, x1 = sch.step(vs[i], t, x, generator=gen, return_dict=False)
+        prevs.append(x)
+        x1s.append(x1)
+    return dict(n=n, S=S, c=2.0, sigmas=sch.sigmas.clone(), timesteps=sch.timesteps.clone(), input_seed=123, noise_seed=777,
+                prev_samples=prevs, predicted_x1=x1s)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
@@ -141,6 +168,7 @@ def main():
     torch.save(tiny_loop(), os.path.join(GOLDEN, "tiny_loop.pt"))
     torch.save(schedules(), os.path.join(GOLDEN, "schedules.pt"))
     torch.save(real_dim_blocks(), os.path.join(GOLDEN, "real_dim_blocks.pt"))
+    torch.save(overshoot_steps(), os.path.join(GOLDEN, "overshoot.pt"))
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

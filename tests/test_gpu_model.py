@@ -186,6 +186,27 @@ def test_schedule_precompute_batch_and_long_schedule():
         eng.step_scheduled(11, inp["latents"], inp["cond"], inp["prompt_embeds"], inp["img_ids"], inp["txt_ids"], 0.5, 0.4)
 
 
+def test_overshoot_scheduler_bit_exact_vs_reference_golden(golden):
+    """TextFlux's default sampler: 6 steps of the reference StochasticRFOvershotDiscreteScheduler (CPU generator seed
+    777) reproduced bit-for-bit by the CUDA step, including predicted_x1."""
+    from textflux_b200 import B200StochasticRFOvershotScheduler, calculate_shift
+    d = golden("overshoot.pt")
+    sch = B200StochasticRFOvershotScheduler()
+    sch.set_c(2.0)
+    sch.set_overshot_func(lambda t, dt: t + dt)
+    mu = calculate_shift(d["S"], 256, 4096, 0.5, 1.15)
+    sch.set_timesteps(sigmas=np.linspace(1.0, 1 / d["n"], d["n"]), device="cuda", mu=mu)
+    g = torch.Generator().manual_seed(d["input_seed"])
+    x = torch.randn(2, d["S"], 64, generator=g).to(torch.bfloat16).cuda()
+    vs = [torch.randn(2, d["S"], 64, generator=g).to(torch.bfloat16).cuda() for _ in range(d["n"])]
+    gen = torch.Generator().manual_seed(d["noise_seed"])
+    for i, t in enumerate(sch.timesteps):
+        x, x1 = sch.step(vs[i], t, x, generator=gen, return_dict=False)
+        assert torch.equal(x.cpu(), d["prev_samples"][i]), i
+        assert torch.equal(x1.cpu(), d["predicted_x1"][i]), i
+    assert sch.step_index == d["n"]
+
+
 def test_engine_input_validation():
     cfg = fo.TINY
     sd = fo.init_state_dict(cfg, seed=1)

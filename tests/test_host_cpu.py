@@ -115,3 +115,40 @@ def test_lora_fold_matches_unfused_math():
     fused = torch.nn.functional.linear(x.float(), W.float())
     unfused = torch.nn.functional.linear(x.float(), ref)
     assert ((fused - unfused).norm() / unfused.norm()).item() < 4e-3
+
+
+def test_overshoot_scheduler_host_arithmetic_matches_reference_golden(golden):
+    """sigmas (float64 shift) and the per-step scalars (t_o - t, a, b) of the overshoot sampler, bit-exact."""
+    from textflux_b200 import B200StochasticRFOvershotScheduler, calculate_shift
+    d = golden("overshoot.pt")
+    sch = B200StochasticRFOvershotScheduler()
+    mu = calculate_shift(d["S"], sch.config.base_image_seq_len, sch.config.max_image_seq_len, sch.config.base_shift,
+                         sch.config.max_shift)
+    sch.set_timesteps(sigmas=np.linspace(1.0, 1 / d["n"], d["n"]), mu=mu)
+    assert torch.equal(sch.sigmas, d["sigmas"]) and torch.equal(sch.timesteps, d["timesteps"])
+    for i in range(d["n"]):
+        coef, a, b, sg = sch._scalars(i)
+        sigma, sn = d["sigmas"][i], d["sigmas"][i + 1]
+        t = 1 - sigma
+        step = sigma - sn
+        tn = min(t + step, 1)
+        to_ = min(tn + step * 2.0, 1)
+        ra = tn / to_
+        rb = ((1 - tn) ** 2 - (ra - tn) ** 2) ** 0.5
+        assert coef == float(to_ - t) and a == float(ra) and b == float(rb) and sg == float(sigma)
+    with pytest.raises(ValueError):
+        sch.set_attn_map(torch.ones(4))
+
+
+def test_oracle_overshoot_step_bit_exact(golden):
+    d = golden("overshoot.pt")
+    sig, ts = fo.overshoot_set_timesteps(d["n"], d["S"])
+    assert torch.equal(sig, d["sigmas"]) and torch.equal(ts, d["timesteps"])
+    g = torch.Generator().manual_seed(d["input_seed"])
+    x = torch.randn(2, d["S"], 64, generator=g).to(torch.bfloat16)
+    vs = [torch.randn(2, d["S"], 64, generator=g).to(torch.bfloat16) for _ in range(d["n"])]
+    gen = torch.Generator().manual_seed(d["noise_seed"])
+    for i in range(d["n"]):
+        eps = torch.randn(x.shape, generator=gen, dtype=torch.float32)
+        x, x1 = fo.overshoot_step(vs[i], sig[i], sig[i + 1], x, eps)
+        assert torch.equal(x, d["prev_samples"][i]) and torch.equal(x1, d["predicted_x1"][i])

@@ -3,11 +3,12 @@
 Public surface (mirrors what the reference pipeline touches):
     B200FluxTransformer           drop-in for FluxTransformer2DModel on `pipe.transformer`
     B200FlowMatchEulerScheduler   drop-in for FlowMatchEulerDiscreteScheduler on `pipe.scheduler`
+    B200StochasticRFOvershotScheduler   drop-in for StochasticRFOvershotDiscreteScheduler (TextFlux's "overshoot" sampler)
     attach(pipe)                  swap both into a loaded FluxFillPipeline
 """
-from .engine import (B200FlowMatchEulerScheduler, B200FluxTransformer, FrozenConfig, attach,  # noqa: F401
-                     calculate_shift)
+from .engine import (B200FlowMatchEulerScheduler, B200FluxTransformer, B200StochasticRFOvershotScheduler,  # noqa: F401
+                     FrozenConfig, attach, calculate_shift)
 from .packer import fold_lora, pack_weights, reference_names, synthetic_getter  # noqa: F401
 
-__all__ = ["B200FluxTransformer", "B200FlowMatchEulerScheduler", "attach", "calculate_shift", "fold_lora",
+__all__ = ["B200FluxTransformer", "B200FlowMatchEulerScheduler", "B200StochasticRFOvershotScheduler", "attach", "calculate_shift", "fold_lora",
            "pack_weights", "reference_names", "synthetic_getter", "FrozenConfig"]

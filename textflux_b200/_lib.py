@@ -30,6 +30,7 @@ SIGNATURES = {
     "tfx_prepare": (C.c_int, [_P, _I32, _I32, _I32]),
     "tfx_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "tfx_euler_step": (C.c_int, [_P, _P, _P, _I64, _F, _F, _P]),
+    "tfx_overshoot_step": (C.c_int, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _P]),
     "tfx_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P]),
     "tfx_set_schedule": (C.c_int, [_P, _P, _I32, _P, _P, _P]),
     "tfx_step_scheduled": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P]),

@@ -206,6 +206,22 @@ __global__ void euler_step_kernel(const __nv_bfloat16* __restrict__ v, const __n
   out[i] = __float2bfloat16_rn(__bfloat162float(x[i]) + dv);
 }
 
+// StochasticRFOvershotDiscreteScheduler.step, attn_map = None (scheduling_stochastic_rf_discrete_overshot.py:339-361):
+//   x_o  = fp32(x) + bf16( bf16(t_o - t) * (-v) )          (0-dim fp32 scalar times bf16 tensor is a bf16 product)
+//   prev = bf16( x_o * a + eps * b )                        (two fp32 products, one fp32 sum, no contraction)
+//   x1   = fp32(x) - bf16( bf16(sigma) * v )
+__global__ void overshoot_step_kernel(const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ x,
+                                      const float* __restrict__ eps, __nv_bfloat16* __restrict__ prev, float* __restrict__ x1,
+                                      long long n, float coef_bf16, float a, float b, float sigma_bf16) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float vf = __bfloat162float(v[i]);
+  const float xf = __bfloat162float(x[i]);
+  const float xo = __fadd_rn(xf, bf16_round(__fmul_rn(coef_bf16, -vf)));
+  prev[i] = __float2bfloat16_rn(__fadd_rn(__fmul_rn(xo, a), __fmul_rn(eps[i], b)));
+  if (x1) x1[i] = __fsub_rn(xf, bf16_round(__fmul_rn(sigma_bf16, vf)));
+}
+
 __global__ void set_float_kernel(float* dst, float value) { *dst = value; }
 
 }  // namespace tfx

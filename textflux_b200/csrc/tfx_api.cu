@@ -1137,6 +1137,24 @@ int tfx_euler_step(const void* model_output, const void* sample, void* prev_samp
   return TFX_OK;
 }
 
+int tfx_overshoot_step(const void* model_output, const void* sample, const void* noise_f32, void* prev_sample,
+                       void* predicted_x1_f32, int64_t n, float t_overshoot_minus_t, float a, float b, float sigma, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(model_output && sample && noise_f32 && prev_sample && n >= 0, TFX_ERR_INVALID, "bad argument");
+    if (n == 0) return TFX_OK;
+    const float coef = __bfloat162float(__float2bfloat16_rn(t_overshoot_minus_t));
+    const float sg = __bfloat162float(__float2bfloat16_rn(sigma));
+    overshoot_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const bf16*>(model_output), reinterpret_cast<const bf16*>(sample), reinterpret_cast<const float*>(noise_f32),
+        reinterpret_cast<bf16*>(prev_sample), reinterpret_cast<float*>(predicted_x1_f32), n, coef, a, b, sg);
+    CUDA_TRY(cudaGetLastError());
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ op-level entry points
 static long long g_op_launches = 0;
 

@@ -426,11 +426,117 @@ class B200FlowMatchEulerScheduler:
         return self.config.num_train_timesteps
 
 
+class B200StochasticRFOvershotScheduler(B200FlowMatchEulerScheduler):
+    """Drop-in for StochasticRFOvershotDiscreteScheduler (scheduling_stochastic_rf_discrete_overshot.py), TextFlux's
+    default "overshoot"/AMO sampler (demo.py:15, run_inference.py:79-91), in the configuration TextFlux uses: attn_map =
+    None and any `overshot_func(t, dt)` evaluated on the host.  Differences from the Euler scheduler it mirrors exactly:
+    `set_timesteps` shifts the pipeline's float64 sigmas in float64 (:203-211), `step` re-noises
+    (x_o * a + eps * b, eps from torch's generator, :351-357) and returns (prev_sample, predicted_x1)."""
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        self.c = 2.0
+        self.overshot_func = lambda t, dt: t + dt
+        self.attn_map = None
+
+    def set_c(self, c: float):
+        self.c = c
+
+    def set_overshot_func(self, overshot_func):
+        self.overshot_func = overshot_func
+
+    def set_attn_map(self, attn_map):
+        if attn_map is not None:
+            raise ValueError("textflux_b200: per-token attn_map overshoot is not part of the TextFlux path")
+
+    def set_timesteps(self, num_inference_steps: int = None, device=None, sigmas=None, mu: Optional[float] = None):
+        if self.config.use_dynamic_shifting and mu is None:
+            raise ValueError(" you have a pass a value for `mu` when `use_dynamic_shifting` is set to be `True`")
+        n_train = self.config.num_train_timesteps
+        if sigmas is None:
+            self.num_inference_steps = num_inference_steps
+            timesteps = np.linspace(self.sigma_max * n_train, self.sigma_min * n_train, num_inference_steps)
+            sigmas = timesteps / n_train
+        sigmas = np.asarray(sigmas)  # no float32 cast here, unlike the Euler scheduler: the shift runs in float64
+        if self.config.use_dynamic_shifting:
+            sigmas = self.time_shift(mu, 1.0, sigmas)
+        else:
+            sigmas = self.config.shift * sigmas / (1 + (self.config.shift - 1) * sigmas)
+        sig = torch.from_numpy(np.asarray(sigmas)).to(dtype=torch.float32)
+        ts = sig * n_train
+        sig = torch.cat([sig, torch.zeros(1)])
+        self._timesteps_cpu = ts.clone()
+        self.sigmas_cpu = sig.tolist()
+        self.timesteps = ts.to(device=device)
+        self.sigmas = sig.to(device=device)
+        self._step_index = None
+        self._begin_index = None
+
+    def _scalars(self, i: int):
+        """(t_o - t, a, b, sigma) in the reference's fp32 0-dim tensor arithmetic (:322-350)."""
+        f = np.float32
+        sigma, sigma_next = f(self.sigmas_cpu[i]), f(self.sigmas_cpu[i + 1])
+        t = f(1) - sigma
+        step = sigma - sigma_next
+        tn = t + step
+        t_next = tn if tn <= 1 else 1
+        so = f(step * f(self.c))
+        to_ = self.overshot_func(t_next, so)
+        to_ = f(to_) if not isinstance(to_, (int,)) else to_
+        t_o = to_ if to_ <= 1 else 1
+        coef = f(f(t_o) - t)
+        a = f(f(t_next) / f(t_o))
+        with np.errstate(invalid="ignore"):
+            r = f(f(f(1) - f(t_next)) * f(f(1) - f(t_next))) - f(f(a - f(t_next)) * f(a - f(t_next)))
+            b = f(np.sqrt(f(r)))
+        return float(coef), float(a), float(b), float(sigma)
+
+    @torch.no_grad()
+    def step(self, model_output: Tensor, timestep, sample: Tensor, s_churn: float = 0.0, s_tmin: float = 0.0,
+             s_tmax: float = float("inf"), s_noise: float = 1.0, generator=None, return_dict: bool = True):
+        if isinstance(timestep, int) or (isinstance(timestep, torch.Tensor)
+                                         and timestep.dtype in (torch.int32, torch.int64)):
+            raise ValueError("Passing integer indices (e.g. from `enumerate(timesteps)`) as timesteps to"
+                             " `EulerDiscreteScheduler.step()` is not supported. Make sure to pass"
+                             " one of the `scheduler.timesteps` as a timestep.")
+        if self._step_index is None:
+            self._init_step_index(timestep)
+        if model_output.device.type != "cuda":
+            raise RuntimeError("textflux_b200: scheduler.step runs on CUDA tensors only (no CPU path)")
+        if model_output.dtype != torch.bfloat16 or model_output.shape != sample.shape:
+            raise ValueError("textflux_b200: scheduler.step expects bf16 model_output with sample's shape")
+        coef, a, b, sigma = self._scalars(self._step_index)
+        v = model_output.contiguous()
+        x = sample.to(torch.bfloat16).contiguous()
+        # randn_tensor(sample.shape, generator, device=sample.device, dtype=float32) (utils/torch_utils.py:38-83): a CPU
+        # generator draws on the CPU and the result is moved, so seeds reproduce across devices
+        if generator is not None and generator.device.type == "cpu":
+            eps = torch.randn(x.shape, generator=generator, dtype=torch.float32).to(x.device)
+        else:
+            eps = torch.randn(x.shape, generator=generator, device=x.device, dtype=torch.float32)
+        prev = torch.empty_like(v)
+        x1 = torch.empty(v.shape, dtype=torch.float32, device=v.device)
+        lib = _lib.load()
+        with torch.cuda.device(v.device):
+            stream = torch.cuda.current_stream(v.device).cuda_stream
+            _lib.check(lib.tfx_overshoot_step(v.data_ptr(), x.data_ptr(), eps.data_ptr(), prev.data_ptr(), x1.data_ptr(),
+                                              v.numel(), coef, a, b, sigma, stream))
+        self._step_index += 1
+        if not return_dict:
+            return (prev, x1)
+        return SimpleNamespace(prev_sample=prev, predicted_x1=x1)
+
+
 def attach(pipe, **engine_kw):
     """Swap the engine into a loaded reference FluxFillPipeline in place (zero edits to reference files):
     `pipe.transformer` -> B200FluxTransformer built from the loaded weights, `pipe.scheduler` -> fused scheduler."""
     eng = B200FluxTransformer.from_reference(pipe.transformer, device=pipe.transformer.device, **engine_kw)
-    sch = B200FlowMatchEulerScheduler.from_config(pipe.scheduler.config)
+    if type(pipe.scheduler).__name__ == "StochasticRFOvershotDiscreteScheduler":
+        sch = B200StochasticRFOvershotScheduler.from_config(pipe.scheduler.config)
+        sch.set_c(getattr(pipe.scheduler, "c", 2.0))
+        sch.set_overshot_func(getattr(pipe.scheduler, "overshot_func", lambda t, dt: t + dt))
+    else:
+        sch = B200FlowMatchEulerScheduler.from_config(pipe.scheduler.config)
     pipe.transformer = eng
     pipe.scheduler = sch
     return pipe
