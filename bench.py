@@ -189,6 +189,10 @@ def run_ours(args, h2, w2, T, desc):
     S, B = h2 * w2, 1
     eng = B200FluxTransformer(cfg, synthetic_getter(cfg, 1234, dev), device=dev, gemm_cta_group=args.cta_group,
                               attn_q_tiles=args.q_tiles, gemm_mcast=args.mcast)
+    if args.pdl >= 0:
+        eng.set_option("use_pdl", args.pdl)
+    if args.attn_variant:
+        eng.set_option("attn_variant", args.attn_variant)
     # ---- synthetic inputs: per-sample seeds; prompt embeds + schedule come from rank 0
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     latents0 = torch.randn(B, S, 64, generator=g, device=dev).to(torch.bfloat16)
@@ -363,6 +367,8 @@ def main():
     ap.add_argument("--mcast", type=int, default=0, help="CTA pairs per cluster sharing A by TMA multicast (0, 2, 4)")
     ap.add_argument("--layers", type=int, default=0, help="debug: override the 19 double blocks (invalidates the number)")
     ap.add_argument("--single-layers", type=int, default=0)
+    ap.add_argument("--pdl", type=int, default=-1, help="override programmatic dependent launch (0/1)")
+    ap.add_argument("--attn-variant", type=int, default=0, help="override the attention schedule (1, 2, 3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-schedule", action="store_true", help="recompute the adaLN modulation every step (drop-in forward semantics)")
     args = ap.parse_args()

@@ -38,7 +38,8 @@ def test_tiny_forward_vs_reference_golden(golden, cta_group, q_tiles, graph, mca
     cfg = fo.FluxConfig(**g["config"])
     sd = fo.init_state_dict(cfg, seed=g["weight_seed"])
     eng = _engine(cfg, sd, gemm_cta_group=cta_group, attn_q_tiles=q_tiles, use_graph=graph, gemm_mcast=mcast)
-    eng.set_option("attn_variant", 1 if mcast == 0 and cta_group == 1 else 2)  # cover both attention schedules
+    eng.set_option("attn_variant", 1 if mcast == 0 and cta_group == 1 else (2 if graph else 3))  # all attention schedules
+    eng.set_option("use_pdl", 0 if (cta_group == 2 and q_tiles == 1) else 1)  # with and without programmatic dependent launch
     inp = _cuda(g["inputs"])
     hs = torch.cat([inp["latents"], inp["cond"]], dim=2)
     for _ in range(2):  # second call replays the captured graph

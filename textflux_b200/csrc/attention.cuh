@@ -92,6 +92,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   const int b = blockIdx.z;
   const int bh = b * p.H + head;
   const int n_kv = (p.N + 127) / 128;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmQ);
@@ -118,6 +119,7 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_ptr;
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
@@ -370,6 +372,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   const int b = blockIdx.z;
   const int bh = b * p.H + head;
   const int n_kv = (p.N + kKV - 1) / kKV;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmQ);
@@ -399,6 +402,7 @@ attention2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_ptr;
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================

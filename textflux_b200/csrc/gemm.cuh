@@ -257,6 +257,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0;
   const bool is_leader = cta_rank == 0;
+  pdl_launch_dependents();  // let the next kernel's CTAs set up (barriers, TMEM) while this grid drains
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA0);
@@ -285,6 +286,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   if constexpr (kCtaGroup == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_ptr;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   // ---- tile schedule (identical in every role)
   const int mt0 = (p.g[0].M + Cfg::kTileM - 1) / Cfg::kTileM;
@@ -441,6 +443,7 @@ gemm_mc_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   const int r = int(rank & 1);
   const bool is_leader = r == 0;
   const uint32_t leader_rank = rank & ~1u;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA0);
@@ -469,6 +472,7 @@ gemm_mc_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_co
   cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_ptr;
+  pdl_wait();
 
   const int mt0 = (p.g[0].M + 255) / 256;
   const int mt1 = (p.num_groups > 1) ? (p.g[1].M + 255) / 256 : 0;

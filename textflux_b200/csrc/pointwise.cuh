@@ -113,6 +113,8 @@ struct LnModParams {
 
 template <int kVec>
 __global__ void __launch_bounds__(128, (kVec <= 12) ? 4 : 2) ln_modulate_kernel(const LnModParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = p.row_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= p.rows) return;
@@ -180,6 +182,8 @@ struct RopeParams {
   float2* out;
 };
 __global__ void rope_table_kernel(const RopeParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int total = (p.T + p.S) * p.half_dim;
   if (idx >= total) return;

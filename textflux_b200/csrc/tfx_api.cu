@@ -149,7 +149,36 @@ struct LaunchCtx {
   long long* counter;
   std::string* err_;
   Profiler* prof = nullptr;
+  bool pdl = false;  // programmatic dependent launch: the kernel may start while its predecessor drains
 };
+
+// <<<>>> with optional launch attributes (PDL, cluster)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, const LaunchCtx& c, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster_x;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (c.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c.stream;
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 struct ProfScope {
   const LaunchCtx& c;
   ProfScope(const LaunchCtx& c_, int fam) : c(c_) { if (c.prof) c.prof->begin(fam, c.stream); }
@@ -205,25 +234,9 @@ void launch_gemm_inst(const LaunchCtx& c, long long tiles, const CUtensorMap& a0
                       const CUtensorMap& b1, const GemmParams& p) {
   std::string* err_ = c.err_;
   const int sms = num_sms(c.device);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cudaLaunchAttribute attr[1];
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.stream = c.stream;
-  cfg.dynamicSmemBytes = GemmCfg<kCG, kBN>::kSmemBytes;
-  if (kCG == 2) {
-    const long long clusters = tiles < sms / 2 ? tiles : sms / 2;
-    cfg.gridDim = dim3((unsigned)(clusters * 2));
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  } else {
-    cfg.gridDim = dim3((unsigned)(tiles < sms ? tiles : sms));
-  }
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<kCG, kBN>, a0, a1, b0, b1, p));
+  long long ctas = (kCG == 2) ? 2 * (tiles < sms / 2 ? tiles : sms / 2) : (tiles < sms ? tiles : sms);
+  CUDA_TRY(launch_ex(gemm_tcgen05_kernel<kCG, kBN>, dim3((unsigned)ctas), dim3(kGemmThreads), GemmCfg<kCG, kBN>::kSmemBytes, c, kCG,
+                     a0, a1, b0, b1, p));
 }
 
 // b0/b1 must be descriptors whose box holds block_n / cta_group rows.
@@ -290,20 +303,8 @@ void launch_gemm_mc_inst(const LaunchCtx& c, long long m_tiles, const CUtensorMa
   const long long supers = m_tiles * ((nt + kPN - 1) / kPN);
   long long clusters = max_mc_clusters<kBN, kPN>(c.device);
   if (supers < clusters) clusters = supers;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
-  cudaLaunchAttribute attr[1];
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.gridDim = dim3((unsigned)(clusters * 2 * kPN));
-  cfg.stream = c.stream;
-  cfg.dynamicSmemBytes = GemmMcCfg<kBN, kPN>::kSmemBytes;
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2 * kPN;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_mc_tcgen05_kernel<kBN, kPN>, a0, a1, b0, b1, p));
+  CUDA_TRY(launch_ex(gemm_mc_tcgen05_kernel<kBN, kPN>, dim3((unsigned)(clusters * 2 * kPN)), dim3(kGemmThreads),
+                     GemmMcCfg<kBN, kPN>::kSmemBytes, c, 2 * kPN, a0, a1, b0, b1, p));
 }
 
 // a0/a1: descriptors with 128/pn-row boxes; b0/b1: block_n/2-row boxes.
@@ -339,7 +340,7 @@ void launch_attention(const LaunchCtx& c, int head_dim, int q_tiles, int emu, co
   ProfScope ps(c, KF_ATTN);
   dim3 grid((p.N + 128 * q_tiles - 1) / (128 * q_tiles), p.H, p.B);
 #define TFX_ATTN(DH, QT, EMU) \
-  attention_tcgen05_kernel<DH, QT, EMU><<<grid, AttnCfg<DH, QT>::kThreads, AttnCfg<DH, QT>::kSmemBytes, c.stream>>>(tq, tk, tv, p)
+  CUDA_TRY(launch_ex(attention_tcgen05_kernel<DH, QT, EMU>, grid, dim3(AttnCfg<DH, QT>::kThreads), AttnCfg<DH, QT>::kSmemBytes, c, 1, tq, tk, tv, p))
   if (head_dim == 128 && q_tiles == 2) {
     switch (emu) {
       case 2: TFX_ATTN(128, 2, 2); break;
@@ -366,9 +367,9 @@ void launch_attention2(const LaunchCtx& c, int head_dim, int mode, const CUtenso
   std::string* err_ = c.err_;
   REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
   ProfScope ps(c, KF_ATTN);
-#define TFX_ATTN2(DH, QT, KV) \
-  attention2_tcgen05_kernel<DH, QT, KV><<<dim3((p.N + 128 * QT - 1) / (128 * QT), p.H, p.B), Attn2Cfg<DH, QT, KV>::kThreads, \
-                                          Attn2Cfg<DH, QT, KV>::kSmemBytes, c.stream>>>(tq, tk, tv, p)
+#define TFX_ATTN2(DH, QT, KV)                                                                                              \
+  CUDA_TRY(launch_ex(attention2_tcgen05_kernel<DH, QT, KV>, dim3((p.N + 128 * QT - 1) / (128 * QT), p.H, p.B),              \
+                     dim3(Attn2Cfg<DH, QT, KV>::kThreads), Attn2Cfg<DH, QT, KV>::kSmemBytes, c, 1, tq, tk, tv, p))
   if (mode == 3) {
     if (head_dim == 128) TFX_ATTN2(128, 1, 128); else TFX_ATTN2(64, 1, 128);
   } else {
@@ -387,12 +388,12 @@ void launch_ln_modulate(const LaunchCtx& c, const LnModParams& p) {
   ProfScope ps(c, KF_LN);
   const int blocks = (rows + 3) / 4;
   switch (p.D / 256) {
-    case 1: ln_modulate_kernel<1><<<blocks, 128, 0, c.stream>>>(p); break;
-    case 2: ln_modulate_kernel<2><<<blocks, 128, 0, c.stream>>>(p); break;
-    case 4: ln_modulate_kernel<4><<<blocks, 128, 0, c.stream>>>(p); break;
-    case 8: ln_modulate_kernel<8><<<blocks, 128, 0, c.stream>>>(p); break;
-    case 12: ln_modulate_kernel<12><<<blocks, 128, 0, c.stream>>>(p); break;
-    case 16: ln_modulate_kernel<16><<<blocks, 128, 0, c.stream>>>(p); break;
+    case 1: CUDA_TRY(launch_ex(ln_modulate_kernel<1>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
+    case 2: CUDA_TRY(launch_ex(ln_modulate_kernel<2>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
+    case 4: CUDA_TRY(launch_ex(ln_modulate_kernel<4>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
+    case 8: CUDA_TRY(launch_ex(ln_modulate_kernel<8>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
+    case 12: CUDA_TRY(launch_ex(ln_modulate_kernel<12>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
+    case 16: CUDA_TRY(launch_ex(ln_modulate_kernel<16>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
     default: REQUIRE(false, TFX_ERR_INVALID, "LayerNorm width %d unsupported", p.D);
   }
   CUDA_TRY(cudaGetLastError());
@@ -435,6 +436,7 @@ struct tfx_model {
   int attn_variant = 1;  // 1: v1 schedule (attn_q_tiles, attn_emu apply); 2: QK-ahead schedule (measured slower)
   int attn_emu = 0;  // exponentials per 8 evaluated on the FMA pipe instead of MUFU (measured slower: softmax is not XU-bound)
   int use_graph = 1;
+  int use_pdl = 1;  // programmatic dependent launch between the kernels of a step (measured -1.5 % step time)
   int profile = 0;
   Profiler prof;
   double prof_us[KF_COUNT] = {0, 0, 0, 0, 0};
@@ -625,8 +627,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     rp.axes[0] = cfg.axes_dims_rope[0]; rp.axes[1] = cfg.axes_dims_rope[1]; rp.axes[2] = cfg.axes_dims_rope[2];
     rp.half_dim = dh / 2; rp.out = rope;
     const int total = N * (dh / 2);
-    rope_table_kernel<<<(total + 255) / 256, 256, 0, c.stream>>>(rp);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_ex(rope_table_kernel, dim3((total + 255) / 256), dim3(256), 0, c, 1, rp));
     ++*c.counter;
   }
   // --- temb + every adaLN `linear(silu(temb))` of the step; with a schedule set they were computed for all steps at
@@ -776,6 +777,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
 
 void tfx_model::run(bool fused_euler, bool want_noise_pred, bool scheduled) {
   LaunchCtx c{stream, device, &launches, err_};
+  c.pdl = use_pdl != 0;
   const int gi = (fused_euler ? 2 : 0) + (scheduled ? 1 : 0);
   if (profile) {
     c.prof = &prof;
@@ -793,6 +795,7 @@ void tfx_model::run(bool fused_euler, bool want_noise_pred, bool scheduled) {
   if (!graphs[gi]) {
     long long scratch = 0;
     LaunchCtx cc{stream, device, &scratch, err_};
+    cc.pdl = use_pdl != 0;
     cudaGraph_t graph = nullptr;
     CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
     try {
@@ -898,6 +901,8 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
     h->attn_emu = (int)value;
   } else if (k == "use_graph") {
     h->use_graph = value != 0;
+  } else if (k == "use_pdl") {
+    h->use_pdl = value != 0;
   } else if (k == "profile") {
     h->profile = value != 0;
     for (int i = 0; i < KF_COUNT; ++i) { h->prof_us[i] = 0; h->prof_n[i] = 0; }

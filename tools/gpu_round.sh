@@ -2,7 +2,7 @@
 # one GPU visit: full gpu test suite, smoke, kernel micro-benchmarks, headline bench, ncu launch list + full captures
 mkdir -p gpurun_out
 R=${1:-r1}
-timeout 1200 python -m pytest tests -m gpu -x -q -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"
+timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider --timeout=120 --timeout-method=thread > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"
 tail -n 5 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -n 2 gpurun_out/smoke.log
 timeout 600 python tools/bench_kernels.py --json gpurun_out/kernels_$R.json > gpurun_out/kernels_$R.log 2>&1; echo "kernels exit $?"
