@@ -44,23 +44,51 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.6e-5, far below
-// the bf16 rounding of P): the softmax is bound by the 16/clk/SM MUFU.EX2 rate, so a fraction of the exponentials is
-// taken off the XU pipe.  x <= ~8 here (scores minus the lazily updated row maximum).
-__device__ __forceinline__ float ex2_emu(float x) {
-  x = fmaxf(x, -125.0f);
-  const float kMagic = 12582912.0f;  // 1.5 * 2^23: adding it rounds x to the nearest integer in the low mantissa bits
-  const float xr = x + kMagic;
-  const float f = x - (xr - kMagic);  // [-0.5, 0.5]
-  const float pf = fmaf(fmaf(fmaf(0.05520550534f, f, 0.24261397123f), f, 0.69325476885f), f, 0.99992769957f);
-  return __int_as_float(__float_as_int(pf) + (__float_as_int(xr) << 23));  // * 2^round(x)
+// A fraction of the softmax exponentials is computed on the FMA pipes (Cody-Waite split + degree-3 minimax
+// polynomial, max relative error 7.6e-5, far below the bf16 rounding of P) to take load off the 16/clk/SM MUFU.EX2
+// unit.  A scalar version of this cost more issue slots than it freed XU cycles (measured -9 %); the packed fp32x2
+// version below gains 4-8 % at 2 pairs in 8 (profiles/r1i_kernels.json).
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): two softmax columns per instruction
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
 }
-
-// kEmu of every 8 exponentials go through ex2_emu (0 = all on MUFU)
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// 2^x for a pair on the packed pipes; x <= ~8 here (scores minus the lazily updated row maximum)
+__device__ __forceinline__ void ex2_emu2(f32x2 x, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  x = pack2(fmaxf(x0, -125.0f), fmaxf(x1, -125.0f));
+  const f32x2 kMagic = pack2(12582912.0f, 12582912.0f), kNegMagic = pack2(-12582912.0f, -12582912.0f);
+  const f32x2 xr = add2(x, kMagic);
+  const f32x2 n = add2(xr, kNegMagic);
+  const f32x2 f = fma2(n, pack2(-1.0f, -1.0f), x);
+  f32x2 pf = fma2(f, pack2(0.05520550534f, 0.05520550534f), pack2(0.24261397123f, 0.24261397123f));
+  pf = fma2(pf, f, pack2(0.69325476885f, 0.69325476885f));
+  pf = fma2(pf, f, pack2(0.99992769957f, 0.99992769957f));
+  float r0, r1, q0, q1;
+  unpack2(xr, r0, r1);
+  unpack2(pf, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
+}
+// kEmu of every 8 column PAIRS go through ex2_emu2 (0 = all on MUFU)
 template <int kEmu>
-__device__ __forceinline__ bool emu_slot(int i) {
-  const int r = i & 7;
-  return (kEmu >= 1 && r == 7) || (kEmu >= 2 && r == 3) || (kEmu >= 3 && r == 5) || (kEmu >= 4 && r == 1);
+__device__ __forceinline__ bool emu_pair(int pair) {
+  const int r = pair & 7;
+  return (kEmu >= 1 && r == 6) || (kEmu >= 2 && r == 2) || (kEmu >= 3 && r == 4) || (kEmu >= 4 && r == 0);
 }
 
 template <int kHeadDim, int kQTiles, int kEmu>
@@ -234,19 +262,27 @@ attention_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       float sum0 = 0.f, sum1 = 0.f;
       uint32_t pk[2][32];
       if (kEmu > 0 && valid >= 128) {
+        const f32x2 c2 = pack2(c, c), nmc2 = pack2(-mc, -mc);
+        f32x2 sum2 = pack2(0.f, 0.f);
 #pragma unroll
         for (int cch = 0; cch < 4; ++cch) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const float x0 = fmaf(__uint_as_float(sr[cch][i]), c, -mc);
-            const float x1 = fmaf(__uint_as_float(sr[cch][i + 1]), c, -mc);
-            const float p0 = emu_slot<kEmu>(i) ? ex2_emu(x0) : ex2(x0);
-            const float p1 = emu_slot<kEmu>(i + 1) ? ex2_emu(x1) : ex2(x1);
-            sum0 += p0;
-            sum1 += p1;
+            const f32x2 x2 = fma2(pack2(__uint_as_float(sr[cch][i]), __uint_as_float(sr[cch][i + 1])), c2, nmc2);
+            float p0, p1;
+            if (emu_pair<kEmu>(i >> 1)) {
+              ex2_emu2(x2, p0, p1);
+            } else {
+              float x0, x1;
+              unpack2(x2, x0, x1);
+              p0 = ex2(x0);
+              p1 = ex2(x1);
+            }
+            sum2 = add2(sum2, pack2(p0, p1));
             pk[cch >> 1][(cch & 1) * 16 + (i >> 1)] = pack_bf16(p0, p1);
           }
         }
+        unpack2(sum2, sum0, sum1);
       } else {
 #pragma unroll
         for (int cch = 0; cch < 4; ++cch) {

@@ -343,6 +343,7 @@ void launch_attention(const LaunchCtx& c, int head_dim, int q_tiles, int emu, co
   CUDA_TRY(launch_ex(attention_tcgen05_kernel<DH, QT, EMU>, grid, dim3(AttnCfg<DH, QT>::kThreads), AttnCfg<DH, QT>::kSmemBytes, c, 1, tq, tk, tv, p))
   if (head_dim == 128 && q_tiles == 2) {
     switch (emu) {
+      case 1:
       case 2: TFX_ATTN(128, 2, 2); break;
       case 3: TFX_ATTN(128, 2, 3); break;
       case 4: TFX_ATTN(128, 2, 4); break;
@@ -434,7 +435,8 @@ struct tfx_model {
   int gemm_mcast = 0;  // 0: plain kernels; 2|4: pairs per cluster sharing A by TMA multicast
   int attn_q_tiles = 2;
   int attn_variant = 1;  // 1: v1 schedule (attn_q_tiles, attn_emu apply); 2: QK-ahead schedule (measured slower)
-  int attn_emu = 0;  // exponentials per 8 evaluated on the FMA pipe instead of MUFU (measured slower: softmax is not XU-bound)
+  int attn_emu = 2;  // column pairs per 8 whose exponentials run on the FMA pipe (packed polynomial) instead of MUFU:
+                     // 2 measured best (+4..8 %), 0 = all MUFU
   int use_graph = 1;
   int use_pdl = 1;  // programmatic dependent launch between the kernels of a step (measured -1.5 % step time)
   int profile = 0;
