@@ -185,8 +185,12 @@ struct ProfScope {
   ~ProfScope() { if (c.prof) c.prof->end(c.stream); }
 };
 
+// cudaFuncSetAttribute is per device: run once for every device a handle (or an op-level call) touches
 void configure_kernels(std::string* err_) {
-  static bool done = false;
+  static std::map<int, bool> done_on;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  bool& done = done_on[dev];
   if (done) return;
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 256>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 256>::kSmemBytes));
