@@ -2,9 +2,9 @@ mkdir -p gpurun_out
 R=${1:-r1f}
 KREG='regex:tcgen05|ln_modulate|gemv_kernel|rope_table|timestep_embed|set_float'
 # warm-up 3 steps (3*292+setup) then one step
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 960 -c 300 --csv --log-file gpurun_out/launches_$R.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREG" -s 951 -c 293 --csv --log-file gpurun_out/launches_$R.csv \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 465 -c 4 -o gpurun_out/prof_gemm_$R -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 467 -c 6 -o gpurun_out/prof_gemm_$R -f \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1; echo "ncu gemm exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_tcgen05 -s 60 -c 2 -o gpurun_out/prof_attn_$R -f \
    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn exit $?"
