@@ -113,41 +113,24 @@ struct LnModParams {
 
 template <int kVec>
 __global__ void __launch_bounds__(128, (kVec <= 12) ? 4 : 2) ln_modulate_kernel(const LnModParams p) {
-  // the block's (shift, scale) vectors go to shared memory with cp.async while the rows are being fetched: the
-  // kernel is a chain of dependent memory latencies (17 rows per SM), not a bandwidth problem
-  extern __shared__ uint4 ln_smem[];  // [2][kVec*32] : shift then scale of the sample of the block's first row
   pdl_launch_dependents();
   pdl_wait();
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int row0 = p.row_begin + blockIdx.x * (blockDim.x >> 5);
-  const int row = row0 + warp;
-  auto sample_of = [&](int r, long long& shift_off, long long& scale_off) {
-    if (r < p.rows0) { shift_off = p.shift0; scale_off = p.scale0; return r / p.rows_per0; }
-    shift_off = p.shift1; scale_off = p.scale1;
-    return (r - p.rows0) / p.rows_per1;
-  };
-  long long sh0, sc0;
-  const int b0 = sample_of(row0, sh0, sc0);
-  {
-    const uint4* gsh = reinterpret_cast<const uint4*>(p.mod + (long long)b0 * p.mod_stride + sh0);
-    const uint4* gsc = reinterpret_cast<const uint4*>(p.mod + (long long)b0 * p.mod_stride + sc0);
-    for (int i = threadIdx.x; i < kVec * 32; i += blockDim.x) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(ln_smem + i)), "l"(gsh + i) : "memory");
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(ln_smem + kVec * 32 + i)), "l"(gsc + i) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  const bool active = row < p.rows;
+  const int row = p.row_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(p.x + (long long)row * p.D);
   uint4 u[kVec];
-  if (active) {
-    const uint4* xr = reinterpret_cast<const uint4*>(p.x + (long long)row * p.D);
 #pragma unroll
-    for (int i = 0; i < kVec; ++i) u[i] = xr[lane + i * 32];
+  for (int i = 0; i < kVec; ++i) u[i] = xr[lane + i * 32];
+  int b;
+  long long shift_off, scale_off;
+  if (row < p.rows0) {
+    b = row / p.rows_per0; shift_off = p.shift0; scale_off = p.scale0;
   } else {
-#pragma unroll
-    for (int i = 0; i < kVec; ++i) u[i] = make_uint4(0, 0, 0, 0);
+    b = (row - p.rows0) / p.rows_per1; shift_off = p.shift1; scale_off = p.scale1;
   }
+  const uint4* sh = reinterpret_cast<const uint4*>(p.mod + (long long)b * p.mod_stride + shift_off);
+  const uint4* sc = reinterpret_cast<const uint4*>(p.mod + (long long)b * p.mod_stride + scale_off);
   float v[kVec * 8];
   float sum = 0.f;
 #pragma unroll
@@ -167,22 +150,13 @@ __global__ void __launch_bounds__(128, (kVec <= 12) ? 4 : 2) ln_modulate_kernel(
     sq = fmaf(v[i], v[i], sq);
   }
   const float rstd = rsqrtf(warp_sum(sq) / float(p.D) + p.eps);
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  if (!active) return;
-  long long sh, sc;
-  const int b = sample_of(row, sh, sc);
-  // rows of a block nearly always share one sample; the rare straddling row reads its vectors from global memory
-  const bool same = (b == b0) && (sh == sh0) && (sc == sc0);
-  const uint4* gsh = reinterpret_cast<const uint4*>(p.mod + (long long)b * p.mod_stride + sh);
-  const uint4* gsc = reinterpret_cast<const uint4*>(p.mod + (long long)b * p.mod_stride + sc);
   uint4* yr = reinterpret_cast<uint4*>(p.y + (long long)row * p.D);
   // fp32 throughout, one rounding at the store (the eager reference rounds to bf16 after each of its four ops; this
   // is never further from the fp32 result than the reference is -- tests/test_gpu_ops.py::test_ln_modulate)
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
-    const uint4 s4 = same ? ln_smem[lane + i * 32] : __ldg(gsh + lane + i * 32);
-    const uint4 c4 = same ? ln_smem[kVec * 32 + lane + i * 32] : __ldg(gsc + lane + i * 32);
+    const uint4 s4 = __ldg(sh + lane + i * 32);
+    const uint4 c4 = __ldg(sc + lane + i * 32);
     const uint32_t su[4] = {s4.x, s4.y, s4.z, s4.w};
     const uint32_t cu[4] = {c4.x, c4.y, c4.z, c4.w};
     uint32_t o[4];

@@ -393,12 +393,12 @@ void launch_ln_modulate(const LaunchCtx& c, const LnModParams& p) {
   ProfScope ps(c, KF_LN);
   const int blocks = (rows + 3) / 4;
   switch (p.D / 256) {
-    case 1: CUDA_TRY(launch_ex(ln_modulate_kernel<1>, dim3(blocks), dim3(128), 1 * 32 * 16 * 2, c, 1, p)); break;
-    case 2: CUDA_TRY(launch_ex(ln_modulate_kernel<2>, dim3(blocks), dim3(128), 2 * 32 * 16 * 2, c, 1, p)); break;
-    case 4: CUDA_TRY(launch_ex(ln_modulate_kernel<4>, dim3(blocks), dim3(128), 4 * 32 * 16 * 2, c, 1, p)); break;
-    case 8: CUDA_TRY(launch_ex(ln_modulate_kernel<8>, dim3(blocks), dim3(128), 8 * 32 * 16 * 2, c, 1, p)); break;
-    case 12: CUDA_TRY(launch_ex(ln_modulate_kernel<12>, dim3(blocks), dim3(128), 12 * 32 * 16 * 2, c, 1, p)); break;
-    case 16: CUDA_TRY(launch_ex(ln_modulate_kernel<16>, dim3(blocks), dim3(128), 16 * 32 * 16 * 2, c, 1, p)); break;
+    case 1: CUDA_TRY(launch_ex(ln_modulate_kernel<1>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
+    case 2: CUDA_TRY(launch_ex(ln_modulate_kernel<2>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
+    case 4: CUDA_TRY(launch_ex(ln_modulate_kernel<4>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
+    case 8: CUDA_TRY(launch_ex(ln_modulate_kernel<8>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
+    case 12: CUDA_TRY(launch_ex(ln_modulate_kernel<12>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
+    case 16: CUDA_TRY(launch_ex(ln_modulate_kernel<16>, dim3(blocks), dim3(128), 0, c, 1, p)); break;
     default: REQUIRE(false, TFX_ERR_INVALID, "LayerNorm width %d unsupported", p.D);
   }
   CUDA_TRY(cudaGetLastError());
