@@ -219,18 +219,14 @@ void configure_kernels(std::string* err_) {
   done = true;
 }
 
-// Tile width that minimises (waves x width) for an [M, N] output on `units` concurrent tiles (SMs or SM pairs).
+// Tile width for an [M, N] output on `units` concurrent tiles (SMs or SM pairs): minimise waves x width, where a narrower
+// tile must win by more than its lower operand reuse costs.  Measured (profiles/r1h_kernels.json, r1i ncu): 224-wide
+// tiles are ~5 % less efficient per column than 256-wide ones, 192-wide ones 15 % (never worth it on these shapes).
 int pick_block_n(long long m_tiles, int N, int units, bool allow_narrow) {
-  int best = 256;
-  long long best_cost = -1;
-  const int cands[3] = {256, 224, 192};
-  for (int i = 0; i < (allow_narrow ? 3 : 1); ++i) {
-    const int bn = cands[i];
-    const long long tiles = m_tiles * ((N + bn - 1) / bn);
-    const long long cost = ((tiles + units - 1) / units) * bn;
-    if (best_cost < 0 || cost < best_cost) { best = bn; best_cost = cost; }
-  }
-  return best;
+  const long long t256 = m_tiles * ((N + 255) / 256), t224 = m_tiles * ((N + 223) / 224);
+  const double c256 = double((t256 + units - 1) / units) * 256.0;
+  const double c224 = double((t224 + units - 1) / units) * 224.0 * 1.05;
+  return (allow_narrow && c224 < c256) ? 224 : 256;
 }
 
 template <int kCG, int kBN>
