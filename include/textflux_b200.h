@@ -112,11 +112,15 @@ int tfx_step_scheduled(tfx_handle h, int32_t step_index, const void* latents_in,
 int tfx_op_linear(const void* A, int64_t lda, const void* W, const void* bias, void* out, int64_t ldo, int32_t M,
                   int32_t N, int32_t K, int32_t mode, const void* gate, const void* res, int32_t cta_group, void* stream);
 /* q,k,v [B,H,N,dh] -> out rows in the engine's [B*T text rows ; B*S image rows] order, row stride ld_out;
- * q_tiles = 3 | 4: QK-ahead schedule (2 query tiles x 64-key tiles | 1 query tile x 128-key tiles); else v1 schedule
- * with q_tiles = tiles + 10 * emu
+ * q_tiles = 3 | 4: QK-ahead schedule (2 query tiles x 64-key tiles | 1 query tile x 128-key tiles);
+ * q_tiles % 10 = 5 | 6: schedule 3 (attention3.cuh; 6 = P handed over in two halves), + 10 * emu, + 100 to trace;
+ * else v1 schedule with q_tiles = tiles + 10 * emu
  * (emu = exponentials per 8 evaluated by the FMA-pipe polynomial: 0, 2, 3, 4) */
 int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int64_t ld_out, int32_t B, int32_t H,
                      int32_t T, int32_t S, int32_t head_dim, int32_t q_tiles, void* stream);
+/* debug: device buffer [n_kv_tiles * 2 * 8] int64 receiving clock64 stamps of CTA (0,0,0) of the schedule-3 attention
+ * kernel when tfx_op_attention is called with q_tiles >= 100 (tools/attn_trace.py); NULL switches it off */
+int tfx_debug_set_attention_trace(void* dev_ptr);
 /* y = LN(x)*(1+scale)+shift per row; mod [B, mod_stride]; rows = B*rows_per_sample */
 int tfx_op_ln_modulate(const void* x, void* y, int32_t rows, int32_t D, int32_t rows_per_sample, const void* mod,
                        int64_t mod_stride, int64_t shift_off, int64_t scale_off, void* stream);

@@ -23,6 +23,7 @@ struct AttnParams {
   float scale_log2;   // dh^-0.5 * log2(e)
   __nv_bfloat16* out;
   long long ld_out;   // row stride of `out` in elements
+  long long* trace = nullptr;  // clock64 stamps of CTA (0,0,0) (attention3 trace builds only; see tools/attn_trace.py)
 };
 
 constexpr int kAttnKvStages = 2;

@@ -14,6 +14,7 @@
 
 #include "../../include/textflux_b200.h"
 #include "attention.cuh"
+#include "attention3.cuh"
 #include "gemm.cuh"
 #include "pointwise.cuh"
 #include "probe.cuh"
@@ -215,6 +216,13 @@ void configure_kernels(std::string* err_) {
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 1>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 2>::kSmemBytes));
+#define TFX_ATTN3_ATTR(DH, EMU, SPLIT, TRACE) \
+  CUDA_TRY(cudaFuncSetAttribute(attention3_tcgen05_kernel<DH, EMU, SPLIT, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg<DH>::kSmemBytes))
+  TFX_ATTN3_ATTR(128, 0, false, false); TFX_ATTN3_ATTR(128, 2, false, false); TFX_ATTN3_ATTR(128, 3, false, false); TFX_ATTN3_ATTR(128, 4, false, false);
+  TFX_ATTN3_ATTR(128, 0, true, false); TFX_ATTN3_ATTR(128, 2, true, false); TFX_ATTN3_ATTR(128, 3, true, false); TFX_ATTN3_ATTR(128, 4, true, false);
+  TFX_ATTN3_ATTR(128, 2, true, true); TFX_ATTN3_ATTR(128, 2, false, true);
+  TFX_ATTN3_ATTR(64, 0, true, false); TFX_ATTN3_ATTR(64, 2, true, false);
+#undef TFX_ATTN3_ATTR
   CUDA_TRY(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   done = true;
 }
@@ -377,6 +385,42 @@ void launch_attention2(const LaunchCtx& c, int head_dim, int mode, const CUtenso
     if (head_dim == 128) TFX_ATTN2(128, 2, 64); else TFX_ATTN2(64, 2, 64);
   }
 #undef TFX_ATTN2
+  CUDA_TRY(cudaGetLastError());
+  ++*c.counter;
+}
+
+// Schedule 3 (attention3.cuh): 2 query tiles per CTA, warp-uniform issuer, split P hand-over, setmaxnreg.
+// emu: exponentials per 8 on the FMA pipe (0, 2, 3, 4); split: hand P over in two halves; trace: clock stamps of CTA 0
+void launch_attention3(const LaunchCtx& c, int head_dim, int emu, bool split, bool trace, const CUtensorMap& tq,
+                       const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p) {
+  std::string* err_ = c.err_;
+  REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
+  ProfScope ps(c, KF_ATTN);
+  dim3 grid((p.N + 255) / 256, p.H, p.B);
+#define TFX_ATTN3(DH, EMU, SPLIT, TRACE) \
+  CUDA_TRY(launch_ex(attention3_tcgen05_kernel<DH, EMU, SPLIT, TRACE>, grid, dim3(Attn3Cfg<DH>::kThreads), Attn3Cfg<DH>::kSmemBytes, c, 1, tq, tk, tv, p))
+  if (head_dim == 128 && trace) {
+    if (split) TFX_ATTN3(128, 2, true, true); else TFX_ATTN3(128, 2, false, true);
+  } else if (head_dim == 128 && split) {
+    switch (emu) {
+      case 1:
+      case 2: TFX_ATTN3(128, 2, true, false); break;
+      case 3: TFX_ATTN3(128, 3, true, false); break;
+      case 4: TFX_ATTN3(128, 4, true, false); break;
+      default: TFX_ATTN3(128, 0, true, false); break;
+    }
+  } else if (head_dim == 128) {
+    switch (emu) {
+      case 1:
+      case 2: TFX_ATTN3(128, 2, false, false); break;
+      case 3: TFX_ATTN3(128, 3, false, false); break;
+      case 4: TFX_ATTN3(128, 4, false, false); break;
+      default: TFX_ATTN3(128, 0, false, false); break;
+    }
+  } else {
+    if (emu) TFX_ATTN3(64, 2, true, false); else TFX_ATTN3(64, 0, true, false);
+  }
+#undef TFX_ATTN3
   CUDA_TRY(cudaGetLastError());
   ++*c.counter;
 }
@@ -689,6 +733,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     }
     if (attn_variant == 2) launch_attention2(c, dh, 2, mQ, mK64, mV64, ap);
     else if (attn_variant == 3) launch_attention2(c, dh, 3, mQ, mK, mV, ap);
+    else if (attn_variant == 4 || attn_variant == 5) launch_attention3(c, dh, attn_emu, attn_variant == 5, false, mQ, mK, mV, ap);
     else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, D);
@@ -743,6 +788,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     }
     if (attn_variant == 2) launch_attention2(c, dh, 2, mQ, mK64, mV64, ap);
     else if (attn_variant == 3) launch_attention2(c, dh, 3, mQ, mK, mV, ap);
+    else if (attn_variant == 4 || attn_variant == 5) launch_attention3(c, dh, attn_emu, attn_variant == 5, false, mQ, mK, mV, ap);
     else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, 5 * D);
@@ -896,7 +942,7 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
     REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
     h->attn_q_tiles = (int)value;
   } else if (k == "attn_variant") {
-    REQUIRE(value >= 1 && value <= 3, TFX_ERR_INVALID, "attn_variant must be 1, 2 or 3");
+    REQUIRE(value >= 1 && value <= 5, TFX_ERR_INVALID, "attn_variant must be 1..5");
     h->attn_variant = (int)value;
   } else if (k == "attn_emu") {
     REQUIRE(value == 0 || (value >= 2 && value <= 4), TFX_ERR_INVALID, "attn_emu must be 0, 2, 3 or 4");
@@ -1202,6 +1248,12 @@ int tfx_op_linear(const void* A, int64_t lda, const void* Wt, const void* bias, 
   return TFX_OK;
 }
 
+static void* g_attn_trace = nullptr;
+int tfx_debug_set_attention_trace(void* dev_ptr) {
+  g_attn_trace = dev_ptr;
+  return TFX_OK;
+}
+
 int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int64_t ld_out, int32_t B, int32_t H, int32_t T,
                      int32_t S, int32_t head_dim, int32_t q_tiles, void* stream) {
   std::string* err_ = nullptr;
@@ -1226,6 +1278,9 @@ int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int
       launch_attention2(c, head_dim, 2, mq, mk64, mv64, p);
     } else if (q_tiles == 4) {
       launch_attention2(c, head_dim, 3, mq, mk, mv, p);
+    } else if (q_tiles % 10 == 5 || q_tiles % 10 == 6) {  // schedule 3: 5 = whole-P hand-over, 6 = split; + 10*emu; + 100 trace
+      p.trace = reinterpret_cast<long long*>(g_attn_trace);
+      launch_attention3(c, head_dim, (q_tiles / 10) % 10, q_tiles % 10 == 6, q_tiles >= 100, mq, mk, mv, p);
     } else {
       launch_attention(c, head_dim, q_tiles % 10, q_tiles / 10, mq, mk, mv, p);
     }
