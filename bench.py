@@ -106,10 +106,11 @@ def dist_env():
 _CPU_CACHE = {}
 
 
-def cpu_reference_sample(h2, w2, T, reps=1):
+def cpu_reference_sample(h2, w2, T, reps=0, budget_s=10.0):
     """The reference's CPU path on this box's host cores, bounded sample: 1 double + 1 single block of the real
-    12B dims at the workload's shape, timed and scaled by the block counts (19 / 38).  Uses the oracle port of the
-    reference forward (bit-exact to the reference on CPU, tests/test_oracle_golden.py)."""
+    12B dims at the workload's shape, repeated to fill about `budget_s` seconds of CPU work (reps = 0) and scaled by
+    the block counts (19 / 38).  Uses the oracle port of the reference forward (bit-exact to the reference on CPU,
+    tests/test_oracle_golden.py)."""
     from oracle import flux_oracle as fo
     cfg = fo.FluxConfig(num_layers=1, num_single_layers=1)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -126,7 +127,11 @@ def cpu_reference_sample(h2, w2, T, reps=1):
     rope = fo.flux_pos_embed(ids, cfg.axes_dims_rope)
     full = fo.FLUX_FILL_12B
     with torch.no_grad():
+        t0 = time.perf_counter()
         fo.double_block(sd, 0, cfg, x, enc, temb, rope)  # warm-up (thread pool, allocator)
+        fo.double_block(sd, 0, cfg, x, enc, temb, rope)
+        if reps <= 0:  # ~2 x reps x (double + single) block times ~= budget
+            reps = max(1, min(200, int(budget_s / max(1e-3, time.perf_counter() - t0))))
         t0 = time.perf_counter()
         for _ in range(reps):
             e2, x2 = fo.double_block(sd, 0, cfg, x, enc, temb, rope)
@@ -139,7 +144,7 @@ def cpu_reference_sample(h2, w2, T, reps=1):
         ts = (time.perf_counter() - t0) / reps
     step_s = full.num_layers * td + full.num_single_layers * ts
     return dict(value=1.0 / step_s, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                sample=f"1 double block ({td:.2f} s) + 1 single block ({ts:.2f} s) of the 12B dims at S={S},T={T}, bf16, "
+                sample=f"{reps} x [1 double block ({td:.2f} s) + 1 single block ({ts:.2f} s)] of the 12B dims at S={S},T={T}, bf16, "
                        f"x{full.num_layers}/x{full.num_single_layers} -> {step_s:.1f} s/step; embedders and scheduler "
                        f"(<0.1%) not timed"), step_s
 

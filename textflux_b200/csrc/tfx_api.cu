@@ -223,6 +223,11 @@ void configure_kernels(std::string* err_) {
   TFX_ATTN3_ATTR(128, 2, true, true); TFX_ATTN3_ATTR(128, 2, false, true);
   TFX_ATTN3_ATTR(64, 0, true, false); TFX_ATTN3_ATTR(64, 2, true, false);
 #undef TFX_ATTN3_ATTR
+#define TFX_ATTN4_ATTR(DH, EMU, TRACE) \
+  CUDA_TRY(cudaFuncSetAttribute(attention3_tcgen05_kernel<DH, EMU, true, TRACE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg<DH>::kSmemBytes))
+  TFX_ATTN4_ATTR(128, 0, false); TFX_ATTN4_ATTR(128, 2, false); TFX_ATTN4_ATTR(128, 3, false); TFX_ATTN4_ATTR(128, 4, false);
+  TFX_ATTN4_ATTR(128, 2, true); TFX_ATTN4_ATTR(64, 0, false); TFX_ATTN4_ATTR(64, 2, false);
+#undef TFX_ATTN4_ATTR
   CUDA_TRY(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   done = true;
 }
@@ -391,12 +396,34 @@ void launch_attention2(const LaunchCtx& c, int head_dim, int mode, const CUtenso
 
 // Schedule 3 (attention3.cuh): 2 query tiles per CTA, warp-uniform issuer, split P hand-over, setmaxnreg.
 // emu: exponentials per 8 on the FMA pipe (0, 2, 3, 4); split: hand P over in two halves; trace: clock stamps of CTA 0
+// rowsplit: two threads per query row, both softmax warpgroups on the same tile (implies the two-barrier hand-over)
 void launch_attention3(const LaunchCtx& c, int head_dim, int emu, bool split, bool trace, const CUtensorMap& tq,
-                       const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p) {
+                       const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, bool rowsplit = false) {
   std::string* err_ = c.err_;
   REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
   ProfScope ps(c, KF_ATTN);
   dim3 grid((p.N + 255) / 256, p.H, p.B);
+  if (rowsplit) {
+#define TFX_ATTN4(DH, EMU, TRACE) \
+  CUDA_TRY(launch_ex(attention3_tcgen05_kernel<DH, EMU, true, TRACE, true>, grid, dim3(Attn3Cfg<DH>::kThreads), Attn3Cfg<DH>::kSmemBytes, c, 1, tq, tk, tv, p))
+    if (head_dim == 128 && trace) {
+      TFX_ATTN4(128, 2, true);
+    } else if (head_dim == 128) {
+      switch (emu) {
+        case 1:
+        case 2: TFX_ATTN4(128, 2, false); break;
+        case 3: TFX_ATTN4(128, 3, false); break;
+        case 4: TFX_ATTN4(128, 4, false); break;
+        default: TFX_ATTN4(128, 0, false); break;
+      }
+    } else {
+      if (emu) TFX_ATTN4(64, 2, false); else TFX_ATTN4(64, 0, false);
+    }
+#undef TFX_ATTN4
+    CUDA_TRY(cudaGetLastError());
+    ++*c.counter;
+    return;
+  }
 #define TFX_ATTN3(DH, EMU, SPLIT, TRACE) \
   CUDA_TRY(launch_ex(attention3_tcgen05_kernel<DH, EMU, SPLIT, TRACE>, grid, dim3(Attn3Cfg<DH>::kThreads), Attn3Cfg<DH>::kSmemBytes, c, 1, tq, tk, tv, p))
   if (head_dim == 128 && trace) {
@@ -478,7 +505,8 @@ struct tfx_model {
   int gemm_cta_group = 1;
   int gemm_mcast = 0;  // 0: plain kernels; 2|4: pairs per cluster sharing A by TMA multicast
   int attn_q_tiles = 2;
-  int attn_variant = 1;  // 1: v1 schedule (attn_q_tiles, attn_emu apply); 2: QK-ahead schedule (measured slower)
+  int attn_variant = 5;  // 1: v1 schedule (attn_q_tiles, attn_emu apply); 2, 3: QK-ahead schedules (measured slower);
+                         // 4, 5, 6: schedule 3 (attention3.cuh) whole-P / split-P (default, fastest) / row-split softmax
   int attn_emu = 2;  // column pairs per 8 whose exponentials run on the FMA pipe (packed polynomial) instead of MUFU:
                      // 2 measured best (+4..8 %), 0 = all MUFU
   int use_graph = 1;
@@ -733,7 +761,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     }
     if (attn_variant == 2) launch_attention2(c, dh, 2, mQ, mK64, mV64, ap);
     else if (attn_variant == 3) launch_attention2(c, dh, 3, mQ, mK, mV, ap);
-    else if (attn_variant == 4 || attn_variant == 5) launch_attention3(c, dh, attn_emu, attn_variant == 5, false, mQ, mK, mV, ap);
+    else if (attn_variant >= 4) launch_attention3(c, dh, attn_emu, attn_variant == 5, false, mQ, mK, mV, ap, attn_variant == 6);
     else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, D);
@@ -788,7 +816,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     }
     if (attn_variant == 2) launch_attention2(c, dh, 2, mQ, mK64, mV64, ap);
     else if (attn_variant == 3) launch_attention2(c, dh, 3, mQ, mK, mV, ap);
-    else if (attn_variant == 4 || attn_variant == 5) launch_attention3(c, dh, attn_emu, attn_variant == 5, false, mQ, mK, mV, ap);
+    else if (attn_variant >= 4) launch_attention3(c, dh, attn_emu, attn_variant == 5, false, mQ, mK, mV, ap, attn_variant == 6);
     else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, 5 * D);
@@ -942,7 +970,7 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
     REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
     h->attn_q_tiles = (int)value;
   } else if (k == "attn_variant") {
-    REQUIRE(value >= 1 && value <= 5, TFX_ERR_INVALID, "attn_variant must be 1..5");
+    REQUIRE(value >= 1 && value <= 6, TFX_ERR_INVALID, "attn_variant must be 1..6");
     h->attn_variant = (int)value;
   } else if (k == "attn_emu") {
     REQUIRE(value == 0 || (value >= 2 && value <= 4), TFX_ERR_INVALID, "attn_emu must be 0, 2, 3 or 4");
@@ -1278,9 +1306,9 @@ int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int
       launch_attention2(c, head_dim, 2, mq, mk64, mv64, p);
     } else if (q_tiles == 4) {
       launch_attention2(c, head_dim, 3, mq, mk, mv, p);
-    } else if (q_tiles % 10 == 5 || q_tiles % 10 == 6) {  // schedule 3: 5 = whole-P hand-over, 6 = split; + 10*emu; + 100 trace
+    } else if (q_tiles % 10 >= 5 && q_tiles % 10 <= 7) {  // schedule 3: 5 = whole-P hand-over, 6 = split, 7 = row-split softmax; + 10*emu; + 100 trace
       p.trace = reinterpret_cast<long long*>(g_attn_trace);
-      launch_attention3(c, head_dim, (q_tiles / 10) % 10, q_tiles % 10 == 6, q_tiles >= 100, mq, mk, mv, p);
+      launch_attention3(c, head_dim, (q_tiles / 10) % 10, q_tiles % 10 == 6, q_tiles >= 100, mq, mk, mv, p, q_tiles % 10 == 7);
     } else {
       launch_attention(c, head_dim, q_tiles % 10, q_tiles / 10, mq, mk, mv, p);
     }
