@@ -253,7 +253,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = (kCtaGroup == 2) ? cluster_ctarank() : 0;
   const bool is_leader = cta_rank == 0;
@@ -325,10 +325,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
+    // The whole warp walks the loop in a warp-uniform context and one elected lane issues: under `lane == 0` the
+    // compiler wraps every tcgen05.mma in a value-broadcast loop (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~15 dependent
+    // instructions per MMA); this way the descriptors live in uniform registers and the MMAs issue back to back.
     if (is_leader) {
       constexpr uint32_t idesc = make_idesc_bf16(Cfg::kTileM, kBN, 0, 0);
+      const bool issuer = elect_one();
+      const uint64_t da0 = make_smem_desc(smem_u32(smem_a), 16, 1024, kLayoutSW128);
+      const uint64_t db0 = make_smem_desc(smem_u32(smem_b), 16, 1024, kLayoutSW128);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -342,21 +348,25 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
           if constexpr (kCtaGroup == 2) mbar_wait_cluster(&full_bar[stage], phase);
           else mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_a + stage * Cfg::kABytes);
-          const uint32_t sb = smem_u32(smem_b + stage * Cfg::kBBytes);
-          const uint64_t da = make_smem_desc(sa, 16, 1024, kLayoutSW128);
-          const uint64_t db = make_smem_desc(sb, 16, 1024, kLayoutSW128);
+          const uint64_t da = da0 + uint64_t(stage * (Cfg::kABytes / 16));
+          const uint64_t db = db0 + uint64_t(stage * (Cfg::kBBytes / 16));
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < kGemmBlockK / 16; ++k) {
-            // +32 bytes (= 2 in 16-byte units) per UMMA_K step inside the 128B swizzle atom
-            umma_ss<kCtaGroup>(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+            for (int k = 0; k < kGemmBlockK / 16; ++k) {
+              // +32 bytes (= 2 in 16-byte units) per UMMA_K step inside the 128B swizzle atom
+              umma_ss<kCtaGroup>(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+            }
+            if constexpr (kCtaGroup == 2) umma_commit_2sm(&empty_bar[stage], 0b11);
+            else umma_commit(&empty_bar[stage]);
           }
-          if constexpr (kCtaGroup == 2) umma_commit_2sm(&empty_bar[stage], 0b11);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if constexpr (kCtaGroup == 2) umma_commit_2sm(&tmem_full_bar[acc], 0b11);
-        else umma_commit(&tmem_full_bar[acc]);
+        if (issuer) {
+          if constexpr (kCtaGroup == 2) umma_commit_2sm(&tmem_full_bar[acc], 0b11);
+          else umma_commit(&tmem_full_bar[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -111,17 +111,26 @@ struct LnModParams {
   float eps;
 };
 
+// The row stays in registers as packed bf16 (kVec uint4 per lane = 48 registers at D = 3072) and is unpacked again in
+// each of the three passes (mean, centred sum of squares, output): an fp32 copy of the row cost 96 more registers,
+// 3 blocks per SM and a second, almost empty wave at 2560 rows (640 blocks on 444 slots); this form keeps 5 blocks
+// per SM resident so the whole grid is one wave.
+// bf16 -> fp32 unpack the compiler may not common up across the three passes (it would keep the fp32 row live)
+__device__ __forceinline__ float lo_nocse(uint32_t u) { float f; asm volatile("shl.b32 %0, %1, 16;" : "=f"(f) : "r"(u)); return f; }
+__device__ __forceinline__ float hi_nocse(uint32_t u) { float f; asm volatile("and.b32 %0, %1, 0xffff0000;" : "=f"(f) : "r"(u)); return f; }
+
+__device__ __forceinline__ uint4 ldg_nc_v4_volatile(const uint4* ptr) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr));
+  return v;
+}
+
 template <int kVec>
-__global__ void __launch_bounds__(128, (kVec <= 12) ? 4 : 2) ln_modulate_kernel(const LnModParams p) {
+__global__ void __launch_bounds__(128, (kVec <= 12) ? 5 : 2) ln_modulate_kernel(const LnModParams p) {
   pdl_launch_dependents();
-  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = p.row_begin + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= p.rows) return;
-  const uint4* xr = reinterpret_cast<const uint4*>(p.x + (long long)row * p.D);
-  uint4 u[kVec];
-#pragma unroll
-  for (int i = 0; i < kVec; ++i) u[i] = xr[lane + i * 32];
   int b;
   long long shift_off, scale_off;
   if (row < p.rows0) {
@@ -131,39 +140,53 @@ __global__ void __launch_bounds__(128, (kVec <= 12) ? 4 : 2) ln_modulate_kernel(
   }
   const uint4* sh = reinterpret_cast<const uint4*>(p.mod + (long long)b * p.mod_stride + shift_off);
   const uint4* sc = reinterpret_cast<const uint4*>(p.mod + (long long)b * p.mod_stride + scale_off);
-  float v[kVec * 8];
+  const uint4* xr = reinterpret_cast<const uint4*>(p.x + (long long)row * p.D);
+  pdl_wait();  // x (and, on the unscheduled path, mod) come from the previous kernels
+  uint4 u[kVec];
+#pragma unroll
+  for (int i = 0; i < kVec; ++i) u[i] = xr[lane + i * 32];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
-    v[8 * i + 0] = bf16_lo(u[i].x); v[8 * i + 1] = bf16_hi(u[i].x);
-    v[8 * i + 2] = bf16_lo(u[i].y); v[8 * i + 3] = bf16_hi(u[i].y);
-    v[8 * i + 4] = bf16_lo(u[i].z); v[8 * i + 5] = bf16_hi(u[i].z);
-    v[8 * i + 6] = bf16_lo(u[i].w); v[8 * i + 7] = bf16_hi(u[i].w);
+    const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) sum += v[8 * i + e];
+    for (int e = 0; e < 4; ++e) sum += lo_nocse(w[e]) + hi_nocse(w[e]);
   }
   const float mean = warp_sum(sum) / float(p.D);
   float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kVec * 8; ++i) {
-    v[i] -= mean;
-    sq = fmaf(v[i], v[i], sq);
+  for (int i = 0; i < kVec; ++i) {
+    const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float d0 = lo_nocse(w[e]) - mean, d1 = hi_nocse(w[e]) - mean;
+      sq = fmaf(d0, d0, sq);
+      sq = fmaf(d1, d1, sq);
+    }
   }
   const float rstd = rsqrtf(warp_sum(sq) / float(p.D) + p.eps);
   uint4* yr = reinterpret_cast<uint4*>(p.y + (long long)row * p.D);
   // fp32 throughout, one rounding at the store (the eager reference rounds to bf16 after each of its four ops; this
   // is never further from the fp32 result than the reference is -- tests/test_gpu_ops.py::test_ln_modulate)
+  // (shift, scale) are fetched two chunks ahead through volatile asm so that the compiler cannot hoist all 2*kVec loads
+  // above the reductions (that costs 96 registers and spills)
+  uint4 s4[2], c4[2];
+  s4[0] = ldg_nc_v4_volatile(sh + lane);
+  c4[0] = ldg_nc_v4_volatile(sc + lane);
 #pragma unroll
   for (int i = 0; i < kVec; ++i) {
-    const uint4 s4 = __ldg(sh + lane + i * 32);
-    const uint4 c4 = __ldg(sc + lane + i * 32);
-    const uint32_t su[4] = {s4.x, s4.y, s4.z, s4.w};
-    const uint32_t cu[4] = {c4.x, c4.y, c4.z, c4.w};
+    if (i + 1 < kVec) {
+      s4[(i + 1) & 1] = ldg_nc_v4_volatile(sh + lane + (i + 1) * 32);
+      c4[(i + 1) & 1] = ldg_nc_v4_volatile(sc + lane + (i + 1) * 32);
+    }
+    const uint32_t w[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+    const uint32_t su[4] = {s4[i & 1].x, s4[i & 1].y, s4[i & 1].z, s4[i & 1].w};
+    const uint32_t cu[4] = {c4[i & 1].x, c4[i & 1].y, c4[i & 1].z, c4[i & 1].w};
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const float y0 = fmaf(v[8 * i + 2 * e] * rstd, 1.0f + bf16_lo(cu[e]), bf16_lo(su[e]));
-      const float y1 = fmaf(v[8 * i + 2 * e + 1] * rstd, 1.0f + bf16_hi(cu[e]), bf16_hi(su[e]));
+      const float y0 = fmaf((lo_nocse(w[e]) - mean) * rstd, 1.0f + bf16_lo(cu[e]), bf16_lo(su[e]));
+      const float y1 = fmaf((hi_nocse(w[e]) - mean) * rstd, 1.0f + bf16_hi(cu[e]), bf16_hi(su[e]));
       o[e] = pack_bf16(y0, y1);
     }
     yr[lane + i * 32] = make_uint4(o[0], o[1], o[2], o[3]);
