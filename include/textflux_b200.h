@@ -49,7 +49,7 @@ int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
 void tfx_destroy(tfx_handle h);
 /* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
 const char* tfx_last_error(tfx_handle h);
-/* "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1..6; 5 = schedule 3 split-P, 6 = schedule 3 row-split), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
+/* "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1..7; 5 = schedule 3 split-P, 6 = schedule 3 row-split, 7 = CTA-pair schedule), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
  * pair per kernel, summed per family; resets the sums) */
 int tfx_set_option(tfx_handle h, const char* key, int64_t value);
 /* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step;
@@ -114,7 +114,7 @@ int tfx_op_linear(const void* A, int64_t lda, const void* W, const void* bias, v
 /* q,k,v [B,H,N,dh] -> out rows in the engine's [B*T text rows ; B*S image rows] order, row stride ld_out;
  * q_tiles = 3 | 4: QK-ahead schedule (2 query tiles x 64-key tiles | 1 query tile x 128-key tiles);
  * q_tiles % 10 = 5 | 6 | 7: schedule 3 (attention3.cuh; 6 = P handed over in two halves, 7 = two threads per score
- * row), + 10 * emu, + 100 to trace;
+ * row), + 10 * emu, + 100 to trace;  q_tiles % 10 = 8: CTA-pair schedule (attention_pair.cuh, head_dim 128), + 10 * emu;
  * else v1 schedule with q_tiles = tiles + 10 * emu
  * (emu = exponentials per 8 evaluated by the FMA-pipe polynomial: 0, 2, 3, 4) */
 int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int64_t ld_out, int32_t B, int32_t H,

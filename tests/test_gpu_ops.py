@@ -171,12 +171,15 @@ def _attention(lib, q, k, v, T, q_tiles):
     return torch.cat([txt, img], dim=1)
 
 
-@pytest.mark.parametrize("q_tiles", [1, 2, 3, 4, 32, 5, 26, 46, 7, 27, 47],
-                         ids=["qt1", "qt2", "ahead", "ahead128", "qt2e3", "s3", "s3split_e2", "s3split_e4", "s3row", "s3row_e2", "s3row_e4"])
+@pytest.mark.parametrize("q_tiles", [1, 2, 3, 4, 32, 5, 26, 46, 7, 27, 47, 8, 28, 48],
+                         ids=["qt1", "qt2", "ahead", "ahead128", "qt2e3", "s3", "s3split_e2", "s3split_e4", "s3row", "s3row_e2", "s3row_e4",
+                              "pair", "pair_e2", "pair_e4"])
 @pytest.mark.parametrize("B,H,T,S,dh", [(1, 2, 128, 128, 128), (1, 24, 512, 2048, 128), (2, 4, 16, 64, 64), (1, 3, 40, 217, 128),
                                           (2, 2, 100, 412, 64), (1, 1, 0, 128, 128), (1, 2, 0, 64, 128), (1, 2, 7, 30, 64),
                                           (1, 2, 512, 4608, 128)])
 def test_attention(lib, B, H, T, S, dh, q_tiles):
+    if q_tiles % 10 == 8 and dh != 128:
+        pytest.skip("the CTA-pair schedule is head_dim 128 only")
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + H * 100 + S + dh)
     N = T + S
     q = torch.randn(B, H, N, dh, generator=g, device="cuda").to(torch.bfloat16)

@@ -165,6 +165,15 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, voi
       : "memory");
 }
 
+// cta_group::2 form of the 3-D load (see tma_load_2d_2sm): tx bytes complete on the pair leader's barrier
+__device__ __forceinline__ void tma_load_3d_2sm(const void* tmap, uint64_t* bar, void* dst, int32_t c0, int32_t c1, int32_t c2, uint64_t hint) {
+  uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
+      : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05
 template <int kCtaGroup>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -205,6 +214,13 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// cta_group::2: A rows of each CTA come from that CTA's own TMEM, B halves from each CTA's shared memory
+__device__ __forceinline__ void umma_ts_2sm(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // Make `bar` track completion of all prior tcgen05.mma of this thread (implies fence::before_thread_sync).

@@ -15,6 +15,7 @@
 #include "../../include/textflux_b200.h"
 #include "attention.cuh"
 #include "attention3.cuh"
+#include "attention_pair.cuh"
 #include "gemm.cuh"
 #include "pointwise.cuh"
 #include "probe.cuh"
@@ -223,6 +224,10 @@ void configure_kernels(std::string* err_) {
   TFX_ATTN3_ATTR(128, 2, true, true); TFX_ATTN3_ATTR(128, 2, false, true);
   TFX_ATTN3_ATTR(64, 0, true, false); TFX_ATTN3_ATTR(64, 2, true, false);
 #undef TFX_ATTN3_ATTR
+  CUDA_TRY(cudaFuncSetAttribute(attention_pair_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPairCfg::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_pair_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPairCfg::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_pair_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPairCfg::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention_pair_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPairCfg::kSmemBytes));
 #define TFX_ATTN4_ATTR(DH, EMU, TRACE) \
   CUDA_TRY(cudaFuncSetAttribute(attention3_tcgen05_kernel<DH, EMU, true, TRACE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg<DH>::kSmemBytes))
   TFX_ATTN4_ATTR(128, 0, false); TFX_ATTN4_ATTR(128, 2, false); TFX_ATTN4_ATTR(128, 3, false); TFX_ATTN4_ATTR(128, 4, false);
@@ -448,6 +453,28 @@ void launch_attention3(const LaunchCtx& c, int head_dim, int emu, bool split, bo
     if (emu) TFX_ATTN3(64, 2, true, false); else TFX_ATTN3(64, 0, true, false);
   }
 #undef TFX_ATTN3
+  CUDA_TRY(cudaGetLastError());
+  ++*c.counter;
+}
+
+// CTA-pair schedule (attention_pair.cuh), head_dim 128 only: one query tile per CTA, clusters of 2, cta_group::2 MMAs.
+// tq / tv: 128-row boxes, tk64: 64-row boxes (each CTA loads half of a K tile).
+void launch_attention_pair(const LaunchCtx& c, int emu, const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMap& tv,
+                           const AttnParams& p) {
+  std::string* err_ = c.err_;
+  ProfScope ps(c, KF_ATTN);
+  const int nq = (p.N + 127) / 128;
+  dim3 grid(2 * ((nq + 1) / 2), p.H, p.B);
+#define TFX_ATTNP(EMU) \
+  CUDA_TRY(launch_ex(attention_pair_tcgen05_kernel<EMU>, grid, dim3(AttnPairCfg::kThreads), AttnPairCfg::kSmemBytes, c, 2, tq, tk64, tv, p))
+  switch (emu) {
+    case 1:
+    case 2: TFX_ATTNP(2); break;
+    case 3: TFX_ATTNP(3); break;
+    case 4: TFX_ATTNP(4); break;
+    default: TFX_ATTNP(0); break;
+  }
+#undef TFX_ATTNP
   CUDA_TRY(cudaGetLastError());
   ++*c.counter;
 }
@@ -761,7 +788,8 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     }
     if (attn_variant == 2) launch_attention2(c, dh, 2, mQ, mK64, mV64, ap);
     else if (attn_variant == 3) launch_attention2(c, dh, 3, mQ, mK, mV, ap);
-    else if (attn_variant >= 4) launch_attention3(c, dh, attn_emu, attn_variant == 5, false, mQ, mK, mV, ap, attn_variant == 6);
+    else if (attn_variant == 7 && dh == 128) launch_attention_pair(c, attn_emu, mQ, mK64, mV, ap);
+    else if (attn_variant >= 4) launch_attention3(c, dh, attn_emu, attn_variant != 4, false, mQ, mK, mV, ap, attn_variant == 6);
     else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, D);
@@ -816,7 +844,8 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     }
     if (attn_variant == 2) launch_attention2(c, dh, 2, mQ, mK64, mV64, ap);
     else if (attn_variant == 3) launch_attention2(c, dh, 3, mQ, mK, mV, ap);
-    else if (attn_variant >= 4) launch_attention3(c, dh, attn_emu, attn_variant == 5, false, mQ, mK, mV, ap, attn_variant == 6);
+    else if (attn_variant == 7 && dh == 128) launch_attention_pair(c, attn_emu, mQ, mK64, mV, ap);
+    else if (attn_variant >= 4) launch_attention3(c, dh, attn_emu, attn_variant != 4, false, mQ, mK, mV, ap, attn_variant == 6);
     else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, 5 * D);
@@ -970,7 +999,7 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
     REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
     h->attn_q_tiles = (int)value;
   } else if (k == "attn_variant") {
-    REQUIRE(value >= 1 && value <= 6, TFX_ERR_INVALID, "attn_variant must be 1..6");
+    REQUIRE(value >= 1 && value <= 7, TFX_ERR_INVALID, "attn_variant must be 1..7");
     h->attn_variant = (int)value;
   } else if (k == "attn_emu") {
     REQUIRE(value == 0 || (value >= 2 && value <= 4), TFX_ERR_INVALID, "attn_emu must be 0, 2, 3 or 4");
@@ -1306,6 +1335,10 @@ int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int
       launch_attention2(c, head_dim, 2, mq, mk64, mv64, p);
     } else if (q_tiles == 4) {
       launch_attention2(c, head_dim, 3, mq, mk, mv, p);
+    } else if (q_tiles % 10 == 8) {  // CTA-pair schedule (head_dim 128), + 10*emu
+      REQUIRE(head_dim == 128, TFX_ERR_INVALID, "the CTA-pair attention schedule needs head_dim 128");
+      CUtensorMap mk64 = make_map_3d(err_, k, (long long)B * H, N, head_dim, 64);
+      launch_attention_pair(c, (q_tiles / 10) % 10, mq, mk64, mv, p);
     } else if (q_tiles % 10 >= 5 && q_tiles % 10 <= 7) {  // schedule 3: 5 = whole-P hand-over, 6 = split, 7 = row-split softmax; + 10*emu; + 100 trace
       p.trace = reinterpret_cast<long long*>(g_attn_trace);
       launch_attention3(c, head_dim, (q_tiles / 10) % 10, q_tiles % 10 == 6, q_tiles >= 100, mq, mk, mv, p, q_tiles % 10 == 7);
