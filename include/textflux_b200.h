@@ -133,6 +133,20 @@ int tfx_op_rope_table(const void* txt_ids, const void* img_ids, int32_t T, int32
                       void* out_f32, void* stream);
 /* sinusoidal embedding [B,256] bf16 of bf16(bf16(t)*1000) */
 int tfx_op_timestep_embed(const void* t, int32_t is_f32, int32_t B, void* out, void* stream);
+/* ---- conditioning glue either side of the loop (pure index permutations, bit-exact) ------------ */
+/* replaces FluxFillPipeline._pack_latents (pipeline_flux_fill.py:1743-1748), optionally preceded by the VAE latent
+ * normalisation `(x - shift_factor) * scaling_factor` of prepare_mask_latents (:1536):
+ *   dst[b, i*(w/2)+j, dst_off + c*4 + di*2 + dj] = f(src[b, c, 2i+di, 2j+dj]);  src [B,C,h,w] bf16 or fp32, dst bf16 rows of stride
+ *   dst_ld elements (so latents, masked-image latents and mask can be packed straight into one [B,S,384] buffer) */
+int tfx_op_pack_latents(const void* src, int32_t src_is_f32, void* dst, int64_t dst_ld, int64_t dst_off, int32_t B, int32_t C,
+                        int32_t h, int32_t w, int32_t affine, float shift, float scale, void* stream);
+/* replaces FluxFillPipeline._unpack_latents (:1752-1765), optionally followed by `x / scaling_factor + shift_factor` (:2127) */
+int tfx_op_unpack_latents(const void* src, int64_t src_ld, void* dst, int32_t B, int32_t C, int32_t h, int32_t w, int32_t affine,
+                          float shift, float scale, void* stream);
+/* replaces the mask reshape + pack of prepare_mask_latents (:1563-1580): mask [B,1,h*vs,w*vs] (bf16 or fp32) ->
+ *   dst[b, i*(w/2)+j, dst_off + (py*vs+px)*4 + di*2 + dj] = mask[b, 0, (2i+di)*vs+py, (2j+dj)*vs+px] */
+int tfx_op_pack_mask(const void* mask, int32_t mask_is_f32, void* dst, int64_t dst_ld, int64_t dst_off, int32_t B, int32_t h,
+                     int32_t w, int32_t vae_scale_factor, void* stream);
 /* raw tcgen05 descriptor probe (bring-up / regression of the UMMA encodings); see tests/test_gpu_ops.py */
 int tfx_op_umma_probe(const void* A, const void* Bm, void* D_f32, int32_t n_dim, int32_t k_dim, int32_t b_mn_major,
                       int32_t a_from_tmem, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep_bytes, void* stream);

@@ -471,6 +471,38 @@ def pack_mask(mask: Tensor, vae_scale_factor: int = 8) -> Tensor:
     return pack_latents(m)
 
 
+def normalize_vae_latents(latents: Tensor, shift_factor: float, scaling_factor: float) -> Tensor:
+    """pipeline_flux_fill.py:1536: `(masked_image_latents - shift_factor) * scaling_factor`, each op in the tensor dtype."""
+    return (latents - shift_factor) * scaling_factor
+
+
+def denormalize_vae_latents(latents: Tensor, shift_factor: float, scaling_factor: float) -> Tensor:
+    """pipeline_flux_fill.py:2127: `(latents / scaling_factor) + shift_factor` (the input of vae.decode)."""
+    return (latents / scaling_factor) + shift_factor
+
+
+def prepare_mask_latents(mask: Tensor, masked_image_latents: Tensor, batch_size: int, num_channels_latents: int,
+                         num_images_per_prompt: int, height: int, width: int, dtype, shift_factor: float,
+                         scaling_factor: float, vae_scale_factor: int = 8) -> Tuple[Tensor, Tensor]:
+    """pipeline_flux_fill.py:1505-1583 in its `masked_image.shape[1] == num_channels_latents` branch (no VAE call):
+    normalise, cast, duplicate per prompt, pack the latents; pixel-unshuffle + pack the mask.  height/width in pixels."""
+    h = 2 * (int(height) // (vae_scale_factor * 2))
+    w = 2 * (int(width) // (vae_scale_factor * 2))
+    mil = normalize_vae_latents(masked_image_latents, shift_factor, scaling_factor).to(dtype=dtype)
+    batch_size = batch_size * num_images_per_prompt
+    if mask.shape[0] < batch_size:
+        if batch_size % mask.shape[0] != 0:
+            raise ValueError("The passed mask and the required batch size don't match.")
+        mask = mask.repeat(batch_size // mask.shape[0], 1, 1, 1)
+    if mil.shape[0] < batch_size:
+        if batch_size % mil.shape[0] != 0:
+            raise ValueError("The passed images and the required batch size don't match.")
+        mil = mil.repeat(batch_size // mil.shape[0], 1, 1, 1)
+    assert mil.shape[1] == num_channels_latents and tuple(mil.shape[2:]) == (h, w)
+    mil = pack_latents(mil)
+    return pack_mask(mask, vae_scale_factor).to(dtype=dtype), mil
+
+
 def denoise_loop(sd, cfg: FluxConfig, latents: Tensor, cond: Tensor, prompt_embeds: Tensor, pooled: Tensor,
                  txt_ids: Tensor, img_ids: Tensor, guidance_scale: float, num_inference_steps: int,
                  record: Optional[list] = None) -> Tensor:

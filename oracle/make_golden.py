@@ -161,6 +161,34 @@ def overshoot_steps():
                 prev_samples=prevs, predicted_x1=x1s)
 
 
+@torch.no_grad()
+def conditioning():
+    """the REAL FluxFillPipeline._pack_latents / _unpack_latents / _prepare_latent_image_ids /
+    prepare_mask_latents (latent-input branch, no VAE) and the :2127 de-normalisation on seeded tensors."""
+    from types import SimpleNamespace
+    from .ref_loader import import_reference
+    d = import_reference()
+    P = d.FluxFillPipeline
+    shift, scale, vs = 0.1159, 0.3611, 8  # FLUX VAE config (diffusers/scripts/convert_flux_to_diffusers.py:299-300)
+    out = dict(shift_factor=shift, scaling_factor=scale, vae_scale_factor=vs, cases=[])
+    for ci, (B, h, w, n_img, mask_dtype) in enumerate([(2, 8, 12, 1, torch.float32), (1, 16, 8, 2, torch.bfloat16), (1, 6, 10, 1, torch.float32)]):
+        g = torch.Generator().manual_seed(4000 + ci)
+        lat = torch.randn(B, 16, h, w, generator=g).to(torch.bfloat16)
+        mil = (torch.randn(B, 16, h, w, generator=g) * 3).to(torch.bfloat16)
+        mask = (torch.rand(B, 1, h * vs, w * vs, generator=g) > 0.5).to(mask_dtype)
+        me = SimpleNamespace(vae_scale_factor=vs, vae=SimpleNamespace(config=SimpleNamespace(shift_factor=shift, scaling_factor=scale)),
+                             _pack_latents=P._pack_latents)
+        mask_p, mil_p = P.prepare_mask_latents(me, mask, mil, B, 16, n_img, h * vs, w * vs, torch.bfloat16, "cpu", None)
+        packed = P._pack_latents(lat, B, 16, h, w)
+        unpacked = P._unpack_latents(packed, h * vs, w * vs, vs)
+        decode_in = (unpacked / scale) + shift
+        ids = P._prepare_latent_image_ids(B, h // 2, w // 2, "cpu", torch.bfloat16)
+        out["cases"].append(dict(B=B, h=h, w=w, num_images_per_prompt=n_img, latents=lat, masked_image_latents=mil, mask=mask,
+                                 mask_packed=mask_p.clone(), masked_image_latents_packed=mil_p.clone(), latents_packed=packed.clone(),
+                                 unpacked=unpacked.clone(), decode_in=decode_in.clone(), img_ids=ids.clone()))
+    return out
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.manual_seed(0)
@@ -169,6 +197,7 @@ def main():
     torch.save(schedules(), os.path.join(GOLDEN, "schedules.pt"))
     torch.save(real_dim_blocks(), os.path.join(GOLDEN, "real_dim_blocks.pt"))
     torch.save(overshoot_steps(), os.path.join(GOLDEN, "overshoot.pt"))
+    torch.save(conditioning(), os.path.join(GOLDEN, "conditioning.pt"))
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

@@ -126,6 +126,23 @@ def test_pack_unpack_index_exact():
     assert pm[0, 1, (3 * 8 + 5) * 4 + 1 * 2 + 0] == m[0, 0, 8 * 1 + 3, 8 * 2 + 5]
 
 
+def test_conditioning_glue_matches_reference_golden(golden):
+    """pack / unpack / mask-pack / VAE (de)normalisation restatements against outputs of the REAL
+    FluxFillPipeline helpers (tests/golden/conditioning.pt, written by oracle/make_golden.py::conditioning)."""
+    d = golden("conditioning.pt")
+    sf, sc, vs = d["shift_factor"], d["scaling_factor"], d["vae_scale_factor"]
+    for c in d["cases"]:
+        H, W = c["h"] * vs, c["w"] * vs
+        mp, lp = fo.prepare_mask_latents(c["mask"], c["masked_image_latents"], c["B"], 16, c["num_images_per_prompt"], H, W,
+                                         torch.bfloat16, sf, sc, vs)
+        assert torch.equal(mp, c["mask_packed"]) and torch.equal(lp, c["masked_image_latents_packed"])
+        assert torch.equal(fo.pack_latents(c["latents"]), c["latents_packed"])
+        un = fo.unpack_latents(c["latents_packed"], H, W, vs)
+        assert torch.equal(un, c["unpacked"]) and torch.equal(un, c["latents"])
+        assert torch.equal(fo.denormalize_vae_latents(un, sf, sc), c["decode_in"])
+        assert torch.equal(fo.prepare_latent_image_ids(c["h"] // 2, c["w"] // 2), c["img_ids"])
+
+
 def test_flop_model_matches_survey():
     for S, tf in [(2048, 37.6650989568), (4608, 84.49265762304), (8192, 165.474467315712)]:
         assert abs(fo.flops_per_step(fo.FLUX_FILL_12B, S, 512) / 1e12 - tf) < 1e-6

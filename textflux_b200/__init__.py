@@ -5,9 +5,12 @@ Public surface (mirrors what the reference pipeline touches)
     B200FlowMatchEulerScheduler   drop-in for FlowMatchEulerDiscreteScheduler on `pipe.scheduler`
     B200StochasticRFOvershotScheduler   drop-in for StochasticRFOvershotDiscreteScheduler (TextFlux's "overshoot" sampler)
     attach(pipe)                  swap both into a loaded FluxFillPipeline
+    conditioning                  pack/unpack/mask-pack kernels mirroring FluxFillPipeline._pack_latents & co
+    loader                        safetensors / LoRA files straight into the packed weight layout
 """
 from .engine import (B200FlowMatchEulerScheduler, B200FluxTransformer, B200StochasticRFOvershotScheduler,  # noqa: F401
                      FrozenConfig, attach, calculate_shift)
+from . import conditioning  # noqa: F401
 from .packer import fold_lora, pack_weights, reference_names, synthetic_getter  # noqa: F401
 
 __all__ = ["B200FluxTransformer", "B200FlowMatchEulerScheduler", "B200StochasticRFOvershotScheduler", "attach", "calculate_shift", "fold_lora",

@@ -16,6 +16,7 @@
 #include "attention.cuh"
 #include "attention3.cuh"
 #include "attention_pair.cuh"
+#include "conditioning.cuh"
 #include "gemm.cuh"
 #include "pointwise.cuh"
 #include "probe.cuh"
@@ -1414,6 +1415,76 @@ int tfx_op_timestep_embed(const void* t, int32_t is_f32, int32_t B, void* out, v
     REQUIRE(t && out && B > 0, TFX_ERR_INVALID, "bad argument");
     timestep_embed_kernel<<<B, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(t, is_f32, B, reinterpret_cast<bf16*>(out));
     CUDA_TRY(cudaGetLastError());
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+static int cond_blocks(long long total) {
+  long long b = (total + 255) / 256;
+  return (int)(b < 1 ? 1 : (b > 148 * 16 ? 148 * 16 : b));  // grid-stride, at most 16 blocks per SM
+}
+
+int tfx_op_pack_latents(const void* src, int32_t src_is_f32, void* dst, int64_t dst_ld, int64_t dst_off, int32_t B, int32_t C,
+                        int32_t h, int32_t w, int32_t affine, float shift, float scale, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(src && dst && B > 0 && C > 0, TFX_ERR_INVALID, "bad argument");
+    REQUIRE(h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, TFX_ERR_INVALID, "latent height %d and width %d must be even (2x2 packing)", h, w);
+    REQUIRE(dst_ld >= dst_off + 4LL * C && dst_ld % 2 == 0 && dst_off % 2 == 0, TFX_ERR_INVALID, "packed row stride %lld too small for offset %lld + %d channels",
+            (long long)dst_ld, (long long)dst_off, 4 * C);
+    const long long total = (long long)B * (h / 2) * (w / 2) * C * 2;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (src_is_f32)
+      pack_latents_kernel<float><<<cond_blocks(total), 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<bf16*>(dst), dst_ld, dst_off, B, C, h, w, affine, shift, scale);
+    else
+      pack_latents_kernel<bf16><<<cond_blocks(total), 256, 0, st>>>(reinterpret_cast<const bf16*>(src), reinterpret_cast<bf16*>(dst), dst_ld, dst_off, B, C, h, w, affine, shift, scale);
+    CUDA_TRY(cudaGetLastError());
+    ++g_op_launches;
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+int tfx_op_unpack_latents(const void* src, int64_t src_ld, void* dst, int32_t B, int32_t C, int32_t h, int32_t w, int32_t affine,
+                          float shift, float scale, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(src && dst && B > 0 && C > 0, TFX_ERR_INVALID, "bad argument");
+    REQUIRE(h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, TFX_ERR_INVALID, "latent height %d and width %d must be even (2x2 packing)", h, w);
+    REQUIRE(src_ld >= 4LL * C && src_ld % 2 == 0, TFX_ERR_INVALID, "packed row stride %lld too small for %d channels", (long long)src_ld, 4 * C);
+    REQUIRE(!affine || scale != 0.f, TFX_ERR_INVALID, "scaling_factor must not be 0");
+    const long long total = (long long)B * C * h * (w / 2);
+    unpack_latents_kernel<<<cond_blocks(total), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const bf16*>(src), src_ld, reinterpret_cast<bf16*>(dst), B, C, h, w, affine, shift, scale);
+    CUDA_TRY(cudaGetLastError());
+    ++g_op_launches;
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+int tfx_op_pack_mask(const void* mask, int32_t mask_is_f32, void* dst, int64_t dst_ld, int64_t dst_off, int32_t B, int32_t h,
+                     int32_t w, int32_t vae_scale_factor, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(mask && dst && B > 0, TFX_ERR_INVALID, "bad argument");
+    REQUIRE(h > 0 && w > 0 && h % 2 == 0 && w % 2 == 0, TFX_ERR_INVALID, "latent height %d and width %d must be even (2x2 packing)", h, w);
+    REQUIRE(vae_scale_factor > 0 && vae_scale_factor <= 16, TFX_ERR_INVALID, "vae_scale_factor %d unsupported", vae_scale_factor);
+    const int ch = vae_scale_factor * vae_scale_factor;
+    REQUIRE(dst_ld >= dst_off + 4LL * ch && dst_ld % 2 == 0 && dst_off % 2 == 0, TFX_ERR_INVALID, "packed row stride %lld too small for offset %lld + %d mask channels",
+            (long long)dst_ld, (long long)dst_off, 4 * ch);
+    const long long total = (long long)B * (h / 2) * (w / 2) * ch * 2;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (mask_is_f32)
+      pack_mask_kernel<float><<<cond_blocks(total), 256, 0, st>>>(reinterpret_cast<const float*>(mask), reinterpret_cast<bf16*>(dst), dst_ld, dst_off, B, h, w, vae_scale_factor);
+    else
+      pack_mask_kernel<bf16><<<cond_blocks(total), 256, 0, st>>>(reinterpret_cast<const bf16*>(mask), reinterpret_cast<bf16*>(dst), dst_ld, dst_off, B, h, w, vae_scale_factor);
+    CUDA_TRY(cudaGetLastError());
+    ++g_op_launches;
   } catch (const Fail& f) {
     return f.code;
   }
