@@ -1,0 +1,112 @@
+"""CPU: safetensors / LoRA loader -- file format against the `safetensors` library, sharded
+checkpoints through the packer bit-exactly, LoRA fold against the manual W + (alpha/r) B A, error behaviour."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import flux_oracle as fo
+from textflux_b200 import fold_lora, pack_weights
+from textflux_b200 import loader as ld
+
+
+def _tiny_sd():
+    return fo.init_state_dict(fo.TINY, seed=77, dtype=torch.bfloat16)
+
+
+def test_reader_and_writer_agree_with_the_safetensors_library(tmp_path):
+    sd = _tiny_sd()
+    sd["extra.f32"] = torch.randn(3, 5)
+    sd["extra.empty"] = torch.empty(0, 4, dtype=torch.float16)
+    mine = str(tmp_path / "mine.safetensors")
+    ld.save_safetensors(sd, mine, metadata={"format": "pt"})
+    with ld.SafetensorsFile(mine) as f:
+        assert sorted(f.keys()) == sorted(sd) and f.metadata == {"format": "pt"}
+        for k, v in sd.items():
+            got = f.get(k)
+            assert got.dtype == v.dtype and tuple(got.shape) == tuple(v.shape) and torch.equal(got, v)
+    st = pytest.importorskip("safetensors.torch")
+    theirs = str(tmp_path / "theirs.safetensors")
+    st.save_file({k: v.contiguous() for k, v in sd.items()}, theirs)
+    with ld.SafetensorsFile(theirs) as f:                      # our reader on the library's file
+        for k, v in sd.items():
+            assert torch.equal(f.get(k), v)
+    back = st.load_file(mine)                                   # the library's reader on our file
+    for k, v in sd.items():
+        assert torch.equal(back[k], v)
+
+
+def test_sharded_checkpoint_packs_bit_exactly(tmp_path):
+    cfg, sd = fo.TINY, _tiny_sd()
+    names = sorted(sd)
+    shards = [names[0::3], names[1::3], names[2::3]]
+    wm = {}
+    for i, part in enumerate(shards):
+        fn = f"diffusion_pytorch_model-{i + 1:05d}-of-00003.safetensors"
+        ld.save_safetensors({k: sd[k] for k in part}, str(tmp_path / fn))
+        wm.update({k: fn for k in part})
+    json.dump({"metadata": {}, "weight_map": wm}, open(tmp_path / ld.SAFE_WEIGHTS_INDEX_NAME, "w"))
+    json.dump(dict(cfg.to_dict(), _class_name="FluxTransformer2DModel"), open(tmp_path / ld.CONFIG_NAME, "w"))
+    ck = ld.Checkpoint(str(tmp_path))
+    assert ck.config["num_layers"] == cfg.num_layers
+    ck.check(cfg)
+    got = pack_weights(cfg, ck.getter("cpu"), "cpu")
+    want = pack_weights(cfg, sd.__getitem__, "cpu")
+    assert got.keys() == want.keys()
+    for k in want:
+        assert torch.equal(got[k], want[k]), k
+    ck.close()
+    # a missing tensor is reported like load_state_dict(strict=True) would
+    os.remove(tmp_path / "diffusion_pytorch_model-00001-of-00003.safetensors")
+    ld.save_safetensors({k: sd[k] for k in shards[0][1:]}, str(tmp_path / "diffusion_pytorch_model-00001-of-00003.safetensors"))
+    wm.pop(shards[0][0])
+    json.dump({"metadata": {}, "weight_map": wm}, open(tmp_path / ld.SAFE_WEIGHTS_INDEX_NAME, "w"))
+    with pytest.raises(ValueError, match="missing"):
+        ld.Checkpoint(str(tmp_path)).check(cfg)
+
+
+def test_lora_file_folds_like_the_manual_formula(tmp_path):
+    cfg, sd = fo.TINY, _tiny_sd()
+    D = cfg.inner_dim
+    g = torch.Generator().manual_seed(5)
+    r = 4
+    lora = {}
+    mods = ["transformer_blocks.0.attn.to_q", "transformer_blocks.1.ff.net.0.proj", "single_transformer_blocks.0.proj_mlp",
+            "single_transformer_blocks.1.proj_out"]
+    for m in mods:
+        o, i = sd[m + ".weight"].shape
+        lora[f"transformer.{m}.lora_A.weight"] = (torch.randn(r, i, generator=g) * 0.05).to(torch.bfloat16)
+        lora[f"transformer.{m}.lora_B.weight"] = (torch.randn(o, r, generator=g) * 0.05).to(torch.bfloat16)
+    lora[f"transformer.{mods[1]}.alpha"] = torch.tensor(8.0)
+    (tmp_path / "lora").mkdir()
+    ld.save_safetensors(lora, str(tmp_path / "lora" / ld.LORA_WEIGHT_NAME_SAFE))
+    got = ld.load_lora_file(str(tmp_path / "lora"))
+    assert got.keys() == lora.keys()
+    get = fold_lora(sd.__getitem__, got, scale=0.5)
+    for m in mods:
+        A, Bm = lora[f"transformer.{m}.lora_A.weight"].float(), lora[f"transformer.{m}.lora_B.weight"].float()
+        alpha = 8.0 if m == mods[1] else float(r)
+        want = (sd[m + ".weight"].float() + 0.5 * alpha / r * (Bm @ A)).to(torch.bfloat16)
+        assert torch.equal(get(m + ".weight"), want)
+    assert torch.equal(get("transformer_blocks.0.attn.to_k.weight"), sd["transformer_blocks.0.attn.to_k.weight"])  # untouched
+    assert D == sd["transformer_blocks.0.attn.to_q.weight"].shape[0]
+    bad = dict(lora)
+    bad.pop(f"transformer.{mods[0]}.lora_B.weight")
+    ld.save_safetensors(bad, str(tmp_path / "bad.safetensors"))
+    with pytest.raises(ValueError, match="lora_B"):
+        ld.load_lora_file(str(tmp_path / "bad.safetensors"))
+
+
+def test_corrupt_files_are_rejected(tmp_path):
+    p = tmp_path / "short.safetensors"
+    p.write_bytes(b"\x01\x02")
+    with pytest.raises(ValueError):
+        ld.SafetensorsFile(str(p))
+    p = tmp_path / "lying.safetensors"
+    h = json.dumps({"w": {"dtype": "BF16", "shape": [4, 4], "data_offsets": [0, 8]}}).encode()
+    p.write_bytes(len(h).to_bytes(8, "little") + h + b"\0" * 8)
+    with pytest.raises(ValueError, match="inconsistent"):
+        ld.SafetensorsFile(str(p))
+    with pytest.raises(FileNotFoundError):
+        ld.Checkpoint(str(tmp_path))
