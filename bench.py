@@ -49,6 +49,22 @@ def peaks():
         return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="B200_PROFILING.md fallback")
 
 
+def measured_traffic():
+    """DRAM bytes of one step's kernels from the newest committed ncu pass (profiles/*_traffic.json, tools/gpu_prof2.sh +
+    tools/traffic_from_ncu.py); None if no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    try:
+        with open(files[-1]) as f:
+            d = json.load(f)
+        return {"bytes": d["dram_bytes_per_step"], "read": d["dram_read_bytes_per_step"], "write": d["dram_write_bytes_per_step"],
+                "file": os.path.relpath(files[-1], ROOT)}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -325,8 +341,12 @@ def run_ours(args, h2, w2, T, desc):
              + cfg.num_layers * 2 * (2 * D * 6 * D) + cfg.num_single_layers * (2 * D * 3 * D) + 2 * D * 2 * D
              + 3 * (2 * 256 * D + 2 * D * D) - 2 * 256 * D + 2 * 768 * D)
     achieved = flops * B * (args.steps / (ms / 1e3)) / 1e12  # per GPU
+    tr = measured_traffic() if args.workload == "cfg2" and B == 1 else None
     roof = {"bound": "tensor", "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s",
-            "frac": achieved / pk["sustained"], "frac_of_burst": achieved / pk["burst"], "traffic": None,
+            "frac": achieved / pk["sustained"], "frac_of_burst": achieved / pk["burst"],
+            "traffic": tr["bytes"] if tr else None,
+            "traffic_note": (f"DRAM read {tr['read'] / 1e9:.1f} GB + write {tr['write'] / 1e9:.1f} GB per launch (= one step), ncu pass in "
+                             f"{tr['file']}; algorithmic minimum 23.8 GB of weights + inputs/outputs") if tr else None,
             "launch": "one sampling step (one CUDA-graph launch: every kernel of forward + fused Euler)",
             "flops_per_launch": flops * B, "peak_source": pk["source"] + ", sustained bf16 figure (timed inside a long step)",
             "kernel_families_us": fam}
