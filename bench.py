@@ -50,7 +50,7 @@ def peaks():
 
 
 def measured_traffic():
-    """DRAM bytes of one step's kernels from the newest committed ncu pass (profiles/*_traffic.json, tools/gpu_prof2.sh +
+    """DRAM bytes of one step's kernels from the newest committed ncu pass (profiles/*_traffic.json, tools/gpu_prof.sh +
     tools/traffic_from_ncu.py); None if no capture is committed."""
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))

@@ -1,5 +1,5 @@
 """DRAM traffic of one denoising step from an ncu `--metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum`
-launch list (tools/gpu_prof2.sh): per kernel family and for the whole step -> JSON that bench.py reports as roofline.traffic.
+launch list (tools/gpu_prof.sh): per kernel family and for the whole step -> JSON that bench.py reports as roofline.traffic.
 Usage: python tools/traffic_from_ncu.py gpurun_out/dram_r1m.csv profiles/r1m_traffic.json"""
 import csv
 import json
