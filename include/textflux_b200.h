@@ -49,7 +49,7 @@ int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
 void tfx_destroy(tfx_handle h);
 /* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
 const char* tfx_last_error(tfx_handle h);
-/* "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1..7; 5 = schedule 3 split-P, 6 = schedule 3 row-split, 7 = CTA-pair schedule), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
+/* "gemm_l2_hints" (0..3: bit 0 activations evict_last, bit 1 weights evict_first in the GEMM's TMA loads), "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1..7; 5 = schedule 3 split-P, 6 = schedule 3 row-split, 7 = CTA-pair schedule), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
  * pair per kernel, summed per family; resets the sums) */
 int tfx_set_option(tfx_handle h, const char* key, int64_t value);
 /* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step;
@@ -99,7 +99,8 @@ int tfx_step(tfx_handle h, const void* latents_in, const void* cond, const void*
 /* Hoists the step-invariant part of the loop: computes temb and all adaLN modulation vectors for every step of a
  * schedule at once (timesteps [n_steps, B] bf16 = t/1000 as the pipeline would pass them per step;
  * embeddings.py:1327-1339 + normalization.py:167,200,363).  Then tfx_step_scheduled(i) is tfx_step for step i without
- * the per-step pass over the 6.5 GB modulation matrix.  Results are bit-identical to tfx_step. */
+ * the per-step pass over the 6.5 GB modulation matrix (the table is filled lazily, 8 rows = steps x samples per pass, when
+ * a step first needs it).  Results are bit-identical to tfx_step. */
 int tfx_set_schedule(tfx_handle h, const void* timesteps_bf16, int32_t n_steps, const void* guidance_f32, const void* pooled,
                      void* stream);
 int tfx_step_scheduled(tfx_handle h, int32_t step_index, const void* latents_in, const void* cond,

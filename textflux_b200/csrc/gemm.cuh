@@ -58,7 +58,7 @@ struct GemmParams {
   const float2* rope;        // [n_joint, head_dim/2] (cos, sin)
   float rms_eps;
   const float* dt_ptr;  // EULER: device scalar float(bf16(sigma_next - sigma))
-  int debug_flags;      // bring-up experiments (0 in production)
+  int debug_flags;      // bit 0: A loads with L2 evict_last, bit 1: B (weight) loads with L2 evict_first
 };
 
 constexpr int kGemmBlockN = 256;  // default tile width; 224 / 192 are instantiated to cut wave quantisation
@@ -302,6 +302,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
+    // activations are re-read by every N tile, each weight tile only by the M tiles running at the same time
+    const uint64_t hint_a = (p.debug_flags & 1) ? kEvictLast : kEvictNormal;
+    const uint64_t hint_b = (p.debug_flags & 2) ? kEvictFirst : kEvictNormal;
     for (int t = first_tile; t < num_tiles; t += tile_step) {
       const int mi = t % MT, ni = t / MT;
       const int grp = (mi < mt0) ? 0 : 1;
@@ -316,11 +319,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         uint8_t* sa = smem_a + stage * Cfg::kABytes;
         uint8_t* sb = smem_b + stage * Cfg::kBBytes;
         if constexpr (kCtaGroup == 2) {
-          tma_load_2d_2sm(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, kEvictNormal);
-          tma_load_2d_2sm(tB, &full_bar[stage], sb, kb * kGemmBlockK, n0, kEvictNormal);
+          tma_load_2d_2sm(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, hint_a);
+          tma_load_2d_2sm(tB, &full_bar[stage], sb, kb * kGemmBlockK, n0, hint_b);
         } else {
-          tma_load_2d(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, kEvictNormal);
-          tma_load_2d(tB, &full_bar[stage], sb, kb * kGemmBlockK, n0, kEvictNormal);
+          tma_load_2d(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, hint_a);
+          tma_load_2d(tB, &full_bar[stage], sb, kb * kGemmBlockK, n0, hint_b);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }

@@ -535,6 +535,7 @@ struct tfx_model {
   int attn_q_tiles = 2;
   int attn_variant = 5;  // 1: v1 schedule (attn_q_tiles, attn_emu apply); 2, 3: QK-ahead schedules (measured slower);
                          // 4, 5, 6: schedule 3 (attention3.cuh) whole-P / split-P (default, fastest) / row-split softmax
+  int gemm_l2_hints = 0;  // bit 0: A (activation) loads evict_last, bit 1: B (weight) loads evict_first (option "gemm_l2_hints")
   int attn_emu = 2;  // column pairs per 8 whose exponentials run on the FMA pipe (packed polynomial) instead of MUFU:
                      // 2 measured best (+4..8 %), 0 = all MUFU
   int use_graph = 1;
@@ -571,7 +572,8 @@ struct tfx_model {
   // schedule-wide modulation table (tfx_set_schedule): [sched_steps * B, mod_rows]
   bf16* mod_table = nullptr;
   int sched_steps = 0;
-  bf16 *sched_g = nullptr, *sched_pooled = nullptr;
+  bf16 *sched_g = nullptr, *sched_pooled = nullptr, *sched_t = nullptr;
+  std::vector<char> sched_pass_done;  // one flag per GEMV pass (kGemvMaxB rows of the table): passes run when first needed
 
   const Weight& W(const std::string& name) {
     auto it = w.find(name);
@@ -606,6 +608,7 @@ struct tfx_model {
     if (mod_table) { cudaFree(mod_table); mod_table = nullptr; }
     if (sched_g) { cudaFree(sched_g); sched_g = nullptr; }
     if (sched_pooled) { cudaFree(sched_pooled); sched_pooled = nullptr; }
+    if (sched_t) { cudaFree(sched_t); sched_t = nullptr; }
     sched_steps = 0;
     B = S = T = N = 0;
   }
@@ -742,6 +745,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
     p.N = Nn; p.K = Kk; p.num_groups = 2; p.n_split = Nn; p.mode0 = EPI_STORE; p.mode1 = EPI_STORE;
     p.D = D; p.head_dim = dh; p.num_heads = H; p.n_joint = N; p.q = q; p.k = k; p.v = v; p.rope = rope;
     p.rms_eps = 1e-6f; p.dt_ptr = dt_dev;
+    p.debug_flags = gemm_l2_hints;
     p.g[0].M = (int)rt; p.g[0].rows_per_sample = T; p.g[0].pos_offset = 0;
     p.g[1].M = (int)ri; p.g[1].rows_per_sample = S; p.g[1].pos_offset = T;
     return p;
@@ -1005,6 +1009,9 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
   } else if (k == "attn_emu") {
     REQUIRE(value == 0 || (value >= 2 && value <= 4), TFX_ERR_INVALID, "attn_emu must be 0, 2, 3 or 4");
     h->attn_emu = (int)value;
+  } else if (k == "gemm_l2_hints") {
+    REQUIRE(value >= 0 && value <= 3, TFX_ERR_INVALID, "gemm_l2_hints must be 0..3");
+    h->gemm_l2_hints = (int)value;
   } else if (k == "use_graph") {
     h->use_graph = value != 0;
   } else if (k == "use_pdl") {
@@ -1179,10 +1186,12 @@ int tfx_set_schedule(tfx_handle h, const void* timesteps_bf16, int32_t n_steps, 
     if (h->mod_table) cudaFree(h->mod_table);
     if (h->sched_g) cudaFree(h->sched_g);
     if (h->sched_pooled) cudaFree(h->sched_pooled);
-    h->mod_table = nullptr; h->sched_g = nullptr; h->sched_pooled = nullptr; h->sched_steps = 0;
+    if (h->sched_t) cudaFree(h->sched_t);
+    h->mod_table = nullptr; h->sched_g = nullptr; h->sched_pooled = nullptr; h->sched_t = nullptr; h->sched_steps = 0;
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->mod_table), (size_t)rows * h->mod_rows * 2));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->sched_g), (size_t)rows * 4 + 256));
     CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->sched_pooled), (size_t)rows * P * 2 + 256));
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->sched_t), (size_t)rows * 2 + 256));
     h->sched_steps = n_steps;
   }
   CUDA_TRY(cudaEventRecord(h->ev_in, user));
@@ -1194,12 +1203,11 @@ int tfx_set_schedule(tfx_handle h, const void* timesteps_bf16, int32_t n_steps, 
       CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<float*>(h->sched_g) + (size_t)st * B, guidance_f32, (size_t)B * 4, cudaMemcpyDeviceToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(h->sched_pooled + (size_t)st * B * P, pooled, (size_t)B * P * 2, cudaMemcpyDeviceToDevice, s));
   }
-  LaunchCtx c{s, h->device, &h->launches, err_};
-  for (long long r0 = 0; r0 < rows; r0 += kGemvMaxB) {
-    const int nr = (int)((rows - r0 < kGemvMaxB) ? rows - r0 : kGemvMaxB);
-    h->enqueue_modulation(c, reinterpret_cast<const bf16*>(timesteps_bf16) + r0, reinterpret_cast<const float*>(h->sched_g) + r0,
-                          h->sched_pooled + r0 * P, nr, h->mod_table + r0 * h->mod_rows);
-  }
+  // The table is filled lazily, one GEMV pass (kGemvMaxB rows = steps x samples) at a time, when tfx_step_scheduled first
+  // needs a row of it: a run that stops after k steps pays for ceil(k*B / 8) passes over the 6.5 GB modulation matrix,
+  // not for the whole schedule.  Same kernels on the same rows, so the values are identical either way.
+  CUDA_TRY(cudaMemcpyAsync(h->sched_t, timesteps_bf16, (size_t)rows * 2, cudaMemcpyDeviceToDevice, s));
+  h->sched_pass_done.assign((size_t)((rows + kGemvMaxB - 1) / kGemvMaxB), 0);
   finish(h, err_, user);
   API_END
 }
@@ -1220,6 +1228,19 @@ int tfx_step_scheduled(tfx_handle h, int32_t step_index, const void* latents_in,
   CUDA_TRY(cudaMemcpy2DAsync(h->x_in, (size_t)Ci * 2, latents_in, (size_t)Cl * 2, (size_t)Cl * 2, rows, cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(cudaMemcpy2DAsync(h->x_in + Cl, (size_t)Ci * 2, cond, (size_t)Cc * 2, (size_t)Cc * 2, rows, cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(h->lat_in, latents_in, rows * Cl * 2, cudaMemcpyDeviceToDevice, s));
+  {
+    const long long total = (long long)h->sched_steps * h->B, P = h->cfg.pooled_projection_dim;
+    const long long first = (long long)step_index * h->B / kGemvMaxB, last = ((long long)(step_index + 1) * h->B - 1) / kGemvMaxB;
+    LaunchCtx c{s, h->device, &h->launches, err_};
+    for (long long g = first; g <= last; ++g) {
+      if (h->sched_pass_done[(size_t)g]) continue;
+      const long long r0 = g * kGemvMaxB;
+      const int nr = (int)((total - r0 < kGemvMaxB) ? total - r0 : kGemvMaxB);
+      h->enqueue_modulation(c, h->sched_t + r0, reinterpret_cast<const float*>(h->sched_g) + r0, h->sched_pooled + r0 * P, nr,
+                            h->mod_table + r0 * h->mod_rows);
+      h->sched_pass_done[(size_t)g] = 1;
+    }
+  }
   CUDA_TRY(cudaMemcpyAsync(h->mod, h->mod_table + (size_t)step_index * h->B * h->mod_rows, (size_t)h->B * h->mod_rows * 2,
                            cudaMemcpyDeviceToDevice, s));
   const float dt = __bfloat162float(__float2bfloat16_rn(sigma_next - sigma));

@@ -12,6 +12,9 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm volatile(
 __device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ uint32_t pack(float a, float b) { uint32_t r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r; }
 __device__ __forceinline__ float max3(float a, float b, float c) { float r; asm volatile("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+__device__ __forceinline__ uint32_t ex2f16x2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint32_t packh(float a, float b) { uint32_t r; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a)); return r; }
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t ex2h2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
 
 constexpr int R = 16;   // independent chains
@@ -42,6 +45,9 @@ __global__ void k(float* out, long long* cyc, float seed) {
       if (MODE == 9) u[i] = u[i] * 0x800000u + u[(i + 1) % R];
       if (MODE == 10) v[i] = fmaf(v[i], v[i], v[i]);
       if (MODE == 11) { u[i] = pack(v[i], __uint_as_float(u[i])); w[i] = fma2(w[i], w[i], w[i]); }
+      if (MODE == 13) u[i] = ex2f16x2(u[i]);
+      if (MODE == 14) { u[i] = packh(v[i], __uint_as_float(u[i])); u[i] = ex2f16x2(u[i]); }
+      if (MODE == 15) u[i] = hadd2(u[i], u[(i + 1) % R]);
       if (MODE == 12) { v[i] = ex2(v[i]); v[i] = max3(v[i], v[(i + 1) % R], seed); }
     }
   }
@@ -79,6 +85,9 @@ int main() {
   run<7>("MUFU + F2FP + FFMA2", 3);
   run<11>("F2FP + FFMA2", 2);
   run<12>("MUFU + FMNMX3", 2);
+  run<13>("MUFU.EX2 f16x2", 1);
+  run<14>("F2FP.F16 + MUFU.EX2 f16x2", 2);
+  run<15>("HADD2", 1);
   cudaError_t e = cudaDeviceSynchronize();
   printf("%s\n", cudaGetErrorString(e));
   return 0;
