@@ -110,3 +110,35 @@ def test_corrupt_files_are_rejected(tmp_path):
         ld.SafetensorsFile(str(p))
     with pytest.raises(FileNotFoundError):
         ld.Checkpoint(str(tmp_path))
+
+
+def test_lora_hot_swap_repacks_only_touched_matrices_bit_exactly():
+    """repack_modules(base + adapter) on an already packed model == pack_weights(fold) from scratch; swapping to a second
+    adapter and unloading restore exactly what a fresh pack would hold (hot-swap without re-packing)."""
+    from textflux_b200 import lora_modules, repack_modules
+    cfg, sd = fo.TINY, _tiny_sd()
+    g = torch.Generator().manual_seed(11)
+
+    def adapter(mods, r=4):
+        out = {}
+        for m in mods:
+            o, i = sd[m + ".weight"].shape
+            out[f"transformer.{m}.lora_A.weight"] = (torch.randn(r, i, generator=g) * 0.05).to(torch.bfloat16)
+            out[f"transformer.{m}.lora_B.weight"] = (torch.randn(o, r, generator=g) * 0.05).to(torch.bfloat16)
+        return out
+
+    l1 = adapter(["transformer_blocks.0.attn.to_k", "single_transformer_blocks.1.proj_mlp", "transformer_blocks.1.ff.net.2"])
+    l2 = adapter(["transformer_blocks.0.attn.to_q", "single_transformer_blocks.0.attn.to_v"])
+    base = pack_weights(cfg, sd.__getitem__, "cpu")
+    P = {k: v.clone() for k, v in base.items()}
+    ptrs = {k: v.data_ptr() for k, v in P.items()}
+    touched = repack_modules(cfg, fold_lora(sd.__getitem__, l1, scale=0.8), P, lora_modules(l1))
+    assert sorted(touched) == ["d0.qkv_x", "d1.ff2_x", "s1.qkvmlp"]
+    want = pack_weights(cfg, fold_lora(sd.__getitem__, l1, scale=0.8), "cpu")
+    assert all(torch.equal(P[k], want[k]) for k in want) and {k: v.data_ptr() for k, v in P.items()} == ptrs
+    # swap: modules of the old adapter go back to base, the new ones are folded
+    repack_modules(cfg, fold_lora(sd.__getitem__, l2), P, set(lora_modules(l1)) | set(lora_modules(l2)))
+    want = pack_weights(cfg, fold_lora(sd.__getitem__, l2), "cpu")
+    assert all(torch.equal(P[k], want[k]) for k in want)
+    repack_modules(cfg, sd.__getitem__, P, lora_modules(l2))
+    assert all(torch.equal(P[k], base[k]) for k in base)

@@ -11,7 +11,7 @@ Public surface (mirrors what the reference pipeline touches)
 from .engine import (B200FlowMatchEulerScheduler, B200FluxTransformer, B200StochasticRFOvershotScheduler,  # noqa: F401
                      FrozenConfig, attach, calculate_shift)
 from . import conditioning  # noqa: F401
-from .packer import fold_lora, pack_weights, reference_names, synthetic_getter  # noqa: F401
+from .packer import fold_lora, lora_modules, pack_weights, packed_layout, reference_names, repack_modules, synthetic_getter  # noqa: F401
 
 __all__ = ["B200FluxTransformer", "B200FlowMatchEulerScheduler", "B200StochasticRFOvershotScheduler", "attach", "calculate_shift", "fold_lora",
-           "pack_weights", "reference_names", "synthetic_getter", "FrozenConfig"]
+           "pack_weights", "packed_layout", "repack_modules", "lora_modules", "reference_names", "synthetic_getter", "FrozenConfig"]

@@ -96,6 +96,7 @@ class B200FluxTransformer(torch.nn.Module):
         if attn_q_tiles is not None:
             self.set_option("attn_q_tiles", attn_q_tiles)
         self._shape: Optional[Tuple[int, int, int]] = None
+        self._lora_modules: set = set()
         self.set_option("use_graph", int(use_graph))
         if gemm_mcast is not None:
             self.set_option("gemm_mcast", gemm_mcast)
@@ -110,6 +111,28 @@ class B200FluxTransformer(torch.nn.Module):
     @classmethod
     def from_state_dict(cls, config, state_dict: Dict[str, Tensor], device="cuda", **kw) -> "B200FluxTransformer":
         return cls(config, state_dict.__getitem__, device=device, **kw)
+
+    # ---- LoRA hot-swap (loaders/lora_pipeline.py: load_lora_weights / unload_lora_weights) ------------------------
+    def load_lora_weights(self, get_base: Callable[[str], Tensor], lora: Dict[str, Tensor], scale: float = 1.0) -> None:
+        """Fold an adapter into the packed weights in place, replacing any adapter folded before.  `get_base(name)` returns
+        the BASE tensor of the reference state dict (e.g. `loader.Checkpoint(path).getter(device)` or
+        `module.state_dict().__getitem__`); only the packed matrices that contain a module touched by the old or the new
+        adapter are rewritten (W + scale * alpha/r * B A in fp32, as at load), every device pointer, TMA descriptor and the
+        captured step graph stay valid."""
+        from .packer import fold_lora, lora_modules, repack_modules
+        mods = set(lora_modules(lora)) | self._lora_modules
+        with torch.cuda.device(self._dev):
+            repack_modules(SimpleNamespace(**self.config), fold_lora(get_base, lora, scale=scale), self._weights, mods)
+            torch.cuda.current_stream(self._dev).synchronize()
+        self._lora_modules = set(lora_modules(lora))
+
+    def unload_lora_weights(self, get_base: Callable[[str], Tensor]) -> None:
+        """Restore the base weights of every module the current adapter touched."""
+        from .packer import repack_modules
+        with torch.cuda.device(self._dev):
+            repack_modules(SimpleNamespace(**self.config), get_base, self._weights, self._lora_modules)
+            torch.cuda.current_stream(self._dev).synchronize()
+        self._lora_modules = set()
 
     # ---- what DiffusionPipeline reads -------------------------------------------------------------------------
     @property

@@ -76,16 +76,17 @@ def _cat_lin(get, names: Iterable[str], device, dtype) -> Tuple[Tensor, Tensor]:
     return w, b
 
 
-def pack_weights(cfg, get: Callable[[str], Tensor], device, dtype=torch.bfloat16) -> Dict[str, Tensor]:
-    """Build the packed layout on `device`.  `get(name)` returns the reference tensor (any device); it is called once
-    per tensor, block by block, so a 12B model never needs a second full copy in memory."""
-    P: Dict[str, Tensor] = {}
+def packed_layout(cfg) -> List[Tuple[str, str, List[str]]]:
+    """The packed layout as data: (packed name, kind, reference module/tensor names) in pack order.
+    kind "lin": `<packed>.w` / `<packed>.b` = row-concatenation of the modules' weights / biases;
+    kind "vec": `<packed>` = one reference tensor reshaped [1, n]."""
+    L: List[Tuple[str, str, List[str]]] = []
 
     def put(name, names):
-        P[name + ".w"], P[name + ".b"] = _cat_lin(get, names, device, dtype)
+        L.append((name, "lin", list(names)))
 
     def vec(name, ref):
-        P[name] = get(ref).to(device=device, dtype=dtype).reshape(1, -1).contiguous()
+        L.append((name, "vec", [ref]))
 
     put("x_embedder", ["x_embedder"])
     put("context_embedder", ["context_embedder"])
@@ -122,7 +123,50 @@ def pack_weights(cfg, get: Callable[[str], Tensor], device, dtype=torch.bfloat16
         mod_names.append(r + "norm.linear")
     mod_names.append("norm_out.linear")
     put("mod", mod_names)
+    return L
+
+
+def pack_weights(cfg, get: Callable[[str], Tensor], device, dtype=torch.bfloat16) -> Dict[str, Tensor]:
+    """Build the packed layout on `device`.  `get(name)` returns the reference tensor (any device); it is called once
+    per tensor, block by block, so a 12B model never needs a second full copy in memory."""
+    P: Dict[str, Tensor] = {}
+    for name, kind, refs in packed_layout(cfg):
+        if kind == "lin":
+            P[name + ".w"], P[name + ".b"] = _cat_lin(get, refs, device, dtype)
+        else:
+            P[name] = get(refs[0]).to(device=device, dtype=dtype).reshape(1, -1).contiguous()
     return P
+
+
+def repack_modules(cfg, get: Callable[[str], Tensor], P: Dict[str, Tensor], modules: Iterable[str]) -> List[str]:
+    """Rewrite IN PLACE the packed matrices that contain any of `modules` (reference module names such as
+    `transformer_blocks.3.attn.to_q`) from `get`; every other packed tensor, and every device pointer, stays as it is.
+    This is the hot-swap path of LoRA adapters: only the rows of a touched module change (its fused neighbours are
+    re-copied bit-exactly).  Returns the packed names rewritten."""
+    modules = set(modules)
+    done = []
+    for name, kind, refs in packed_layout(cfg):
+        if kind != "lin" or not modules.intersection(refs):
+            continue
+        row = 0
+        w = P[name + ".w"]
+        for ref in refs:
+            n = get(ref + ".weight")
+            if ref in modules:
+                w[row:row + n.shape[0]].copy_(n.to(device=w.device, dtype=w.dtype))
+            row += n.shape[0]
+        done.append(name)
+    return done
+
+
+def lora_modules(lora: Dict[str, Tensor], prefix: str = "transformer.") -> List[str]:
+    """Reference module names an adapter state dict touches."""
+    out = []
+    for k in lora:
+        if k.endswith(".lora_A.weight"):
+            m = k[: -len(".lora_A.weight")]
+            out.append(m[len(prefix):] if m.startswith(prefix) else m)
+    return out
 
 
 def fold_lora(get: Callable[[str], Tensor], lora: Dict[str, Tensor], scale: float = 1.0,
