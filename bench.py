@@ -216,6 +216,8 @@ def run_ours(args, h2, w2, T, desc):
         eng.set_option("attn_variant", args.attn_variant)
     if args.l2_hints >= 0:
         eng.set_option("gemm_l2_hints", args.l2_hints)
+    if args.narrow_tiles >= 0:
+        eng.set_option("gemm_narrow_tiles", args.narrow_tiles)
     # ---- synthetic inputs: per-sample seeds; prompt embeds + schedule come from rank 0
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     latents0 = torch.randn(B, S, 64, generator=g, device=dev).to(torch.bfloat16)
@@ -396,6 +398,7 @@ def main():
     ap.add_argument("--single-layers", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=-1, help="override programmatic dependent launch (0/1)")
     ap.add_argument("--attn-variant", type=int, default=0, help="override the attention schedule (1, 2, 3)")
+    ap.add_argument("--narrow-tiles", type=int, default=-1, help="override: allow 224-wide GEMM tiles (0/1)")
     ap.add_argument("--l2-hints", type=int, default=-1, help="override the GEMM L2 eviction hints (0..3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-schedule", action="store_true", help="recompute the adaLN modulation every step (drop-in forward semantics)")

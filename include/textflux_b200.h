@@ -49,7 +49,7 @@ int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
 void tfx_destroy(tfx_handle h);
 /* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
 const char* tfx_last_error(tfx_handle h);
-/* "gemm_l2_hints" (0..3: bit 0 activations evict_last, bit 1 weights evict_first in the GEMM's TMA loads), "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1..7; 5 = schedule 3 split-P, 6 = schedule 3 row-split, 7 = CTA-pair schedule), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
+/* "gemm_narrow_tiles" (0|1: allow 224-wide GEMM tiles against wave quantisation), "gemm_l2_hints" (0..3: bit 0 activations evict_last, bit 1 weights evict_first in the GEMM's TMA loads), "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1..7; 5 = schedule 3 split-P, 6 = schedule 3 row-split, 7 = CTA-pair schedule), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
  * pair per kernel, summed per family; resets the sums) */
 int tfx_set_option(tfx_handle h, const char* key, int64_t value);
 /* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step;

@@ -535,6 +535,7 @@ struct tfx_model {
   int attn_q_tiles = 2;
   int attn_variant = 5;  // 1: v1 schedule (attn_q_tiles, attn_emu apply); 2, 3: QK-ahead schedules (measured slower);
                          // 4, 5, 6: schedule 3 (attention3.cuh) whole-P / split-P (default, fastest) / row-split softmax
+  int gemm_narrow_tiles = 1;  // allow 224-wide tiles where they cut wave quantisation (option "gemm_narrow_tiles")
   int gemm_l2_hints = 0;  // bit 0: A (activation) loads evict_last, bit 1: B (weight) loads evict_first (option "gemm_l2_hints")
   int attn_emu = 2;  // column pairs per 8 whose exponentials run on the FMA pipe (packed polynomial) instead of MUFU:
                      // 2 measured best (+4..8 %), 0 = all MUFU
@@ -594,7 +595,7 @@ struct tfx_model {
   int block_n_for(int Nn) const {
     const int tile_m = 128 * gemm_cta_group;
     const long long mt = ((long long)B * T + tile_m - 1) / tile_m + ((long long)B * S + tile_m - 1) / tile_m;
-    const int bn = pick_block_n(mt, Nn, num_sms(device) / gemm_cta_group, true);
+    const int bn = pick_block_n(mt, Nn, num_sms(device) / gemm_cta_group, gemm_narrow_tiles != 0);
     return (gemm_mcast >= 2 && bn == 192) ? 256 : bn;
   }
   void drop_graphs() {
@@ -1009,6 +1010,9 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
   } else if (k == "attn_emu") {
     REQUIRE(value == 0 || (value >= 2 && value <= 4), TFX_ERR_INVALID, "attn_emu must be 0, 2, 3 or 4");
     h->attn_emu = (int)value;
+  } else if (k == "gemm_narrow_tiles") {
+    h->gemm_narrow_tiles = value != 0;
+    h->free_workspace();  // B-side descriptors depend on the tile width: the next tfx_prepare rebuilds them
   } else if (k == "gemm_l2_hints") {
     REQUIRE(value >= 0 && value <= 3, TFX_ERR_INVALID, "gemm_l2_hints must be 0..3");
     h->gemm_l2_hints = (int)value;
