@@ -214,6 +214,8 @@ def run_ours(args, h2, w2, T, desc):
         eng.set_option("use_pdl", args.pdl)
     if args.attn_variant:
         eng.set_option("attn_variant", args.attn_variant)
+    if args.attn_emu >= 0:
+        eng.set_option("attn_emu", args.attn_emu)
     if args.l2_hints >= 0:
         eng.set_option("gemm_l2_hints", args.l2_hints)
     if args.narrow_tiles >= 0:
@@ -398,6 +400,7 @@ def main():
     ap.add_argument("--single-layers", type=int, default=0)
     ap.add_argument("--pdl", type=int, default=-1, help="override programmatic dependent launch (0/1)")
     ap.add_argument("--attn-variant", type=int, default=0, help="override the attention schedule (1, 2, 3)")
+    ap.add_argument("--attn-emu", type=int, default=-1, help="override: softmax column pairs per 8 on the FMA-pipe exp2 (0, 2, 3, 4)")
     ap.add_argument("--narrow-tiles", type=int, default=-1, help="override: allow 224-wide GEMM tiles (0/1)")
     ap.add_argument("--l2-hints", type=int, default=-1, help="override the GEMM L2 eviction hints (0..3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
