@@ -49,10 +49,11 @@ int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
 void tfx_destroy(tfx_handle h);
 /* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
 const char* tfx_last_error(tfx_handle h);
-/* "gemm_narrow_tiles" (0|1: allow 224-wide GEMM tiles against wave quantisation), "gemm_l2_hints" (0..3: bit 0 activations evict_last, bit 1 weights evict_first in the GEMM's TMA loads), "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1..7; 5 = schedule 3 split-P, 6 = schedule 3 row-split, 7 = CTA-pair schedule), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
+/* "gemm_narrow_tiles" (0|1: allow 224-wide GEMM tiles against wave quantisation), "gemm_l2_hints" (0..3: bit 0 activations evict_last, bit 1 weights evict_first in the GEMM's TMA loads), "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1..7; 5 = schedule 3 split-P, 6 = schedule 3 row-split, 7 = CTA-pair schedule), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "mod_cache_slots" (0..4096: device-side cache of modulation vectors keyed on the (timestep, guidance, pooled) bits tfx_forward / tfx_step receive; 0 = recompute every call), "mod_cache_reset" (drop every cached modulation vector: call after rewriting weights in place), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
  * pair per kernel, summed per family; resets the sums) */
 int tfx_set_option(tfx_handle h, const char* key, int64_t value);
 /* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step;
+ * "mod_cache_hits" / "mod_cache_valid": forwards served from the modulation cache / slots in use;
  * "prof_us_<fam>" / "prof_n_<fam>" with fam in gemm|attn|ln|gemv|misc: device microseconds / launches in profile mode */
 int tfx_get_counter(tfx_handle h, const char* key, int64_t* value);
 
@@ -112,6 +113,18 @@ int tfx_step_scheduled(tfx_handle h, int32_t step_index, const void* latents_in,
  * cta_group: 1 | 2 plain kernels, 22 | 24 multicast kernel with 2 | 4 CTA pairs per cluster */
 int tfx_op_linear(const void* A, int64_t lda, const void* W, const void* bias, void* out, int64_t ldo, int32_t M,
                   int32_t N, int32_t K, int32_t mode, const void* gate, const void* res, int32_t cta_group, void* stream);
+/* The fused QKV projection of one stream, as the engine launches it for attention_processor.py:1987-2037: Y = A W^T + bias
+ * with W [3*H*dh, K] = to_q;to_k;to_v, then per head RMSNorm(q), RMSNorm(k) (normalization.py:532-549, weights rms_q/rms_k
+ * [dh]) and apply_rotary_emb (embeddings.py:879-925) with the (cos,sin) table rope_f32 [n_joint, dh/2, 2], scattered
+ * head-major: row m of A is token pos_offset + m % rows_per_sample of sample m / rows_per_sample in q,k,v [*,H,n_joint,dh]. */
+int tfx_op_linear_qkv(const void* A, int64_t lda, const void* W, const void* bias, const void* rms_q, const void* rms_k,
+                      const void* rope_f32, void* q, void* k, void* v, int32_t M, int32_t K, int32_t H, int32_t head_dim,
+                      int32_t rows_per_sample, int32_t pos_offset, int32_t n_joint, int32_t cta_group, void* stream);
+/* proj_out with the scheduler step fused on its store (transformer_flux.py:1203 + scheduling_flow_match_euler_discrete.py:322-330):
+ * v = bf16(A W^T + bias) -> noise_pred_out [M,N] (NULL to skip); latents_out = bf16(latents_in + bf16(dt * v)) with
+ * dt_f32_dev a DEVICE scalar holding float(bf16(sigma_next - sigma)). */
+int tfx_op_linear_euler(const void* A, int64_t lda, const void* W, const void* bias, const void* latents_in, const void* dt_f32_dev,
+                        void* noise_pred_out, void* latents_out, int32_t M, int32_t N, int32_t K, int32_t cta_group, void* stream);
 /* q,k,v [B,H,N,dh] -> out rows in the engine's [B*T text rows ; B*S image rows] order, row stride ld_out;
  * q_tiles = 3 | 4: QK-ahead schedule (2 query tiles x 64-key tiles | 1 query tile x 128-key tiles);
  * q_tiles % 10 = 5 | 6 | 7: schedule 3 (attention3.cuh; 6 = P handed over in two halves, 7 = two threads per score

@@ -138,6 +138,122 @@ def test_linear_narrow_tiles(lib, monkeypatch, bn, cta_group):
         assert _rel(_linear(lib, A, W, b, 2, cta_group, gate=gate, res=res), res + gate * lin.to(torch.bfloat16)) < 4e-3
 
 
+# BASELINE configs 3 / 4 / 5 (and the 12 288-token reading of config 5): more M tiles than CTA pairs, different wave
+# tails than the M = 2560 the tile heuristic was tuned on
+LARGE_M = [(4608, 3072, 3072), (5120, 3072, 3072), (5120, 12288, 3072), (5120, 3072, 12288), (8704, 3072, 3072),
+           (8704, 21504, 3072), (8704, 3072, 15360), (12800, 3072, 3072), (12800, 12288, 3072)]
+
+
+@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
+@pytest.mark.parametrize("M,N,K", LARGE_M)
+def test_linear_large_m(lib, M, N, K, cta_group):
+    if cta_group == 1 and N > 3072:
+        pytest.skip("single-CTA kernel: narrow shapes only (time)")
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    b = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+    gate = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+    res = torch.randn(M, N, generator=g, device="cuda").to(torch.bfloat16)
+    lin = A.float() @ W.float().T + b.float()
+    assert _rel(_linear(lib, A, W, b, 0, cta_group), lin) < 4e-3
+    out = _linear(lib, A, W, b, 2, cta_group, gate=gate, res=res)
+    assert _rel(out, res + gate * lin.to(torch.bfloat16)) < 4e-3
+    del lin
+
+
+def _ref_qkv(A, W, b, rms_q, rms_k, cos, sin, H, dh):
+    """The reference's op sequence for one stream (attention_processor.py:1987-2037): Linear -> view heads -> RMSNorm
+    (normalization.py:532-549) -> apply_rotary_emb (embeddings.py:879-925, use_real_unbind_dim=-1), in eager bf16."""
+    lin = torch.nn.functional.linear(A, W, b)  # bf16
+    M = A.shape[0]
+    q, k, v = lin.view(M, 3, H, dh).unbind(1)
+
+    def rms(x, w):
+        var = x.float().pow(2).mean(-1, keepdim=True)
+        return (x.float() * torch.rsqrt(var + 1e-6)).to(torch.bfloat16) * w
+
+    def rot(x):
+        xr, xi = x.reshape(M, H, dh // 2, 2).unbind(-1)
+        xrot = torch.stack([-xi, xr], dim=-1).flatten(2)
+        return (x.float() * cos[:, None] + xrot.float() * sin[:, None]).to(torch.bfloat16)
+
+    return rot(rms(q, rms_q)), rot(rms(k, rms_k)), v
+
+
+@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
+@pytest.mark.parametrize("Bs,rows,pos0,n_joint,H,dh,K", [(1, 300, 40, 340, 4, 64, 256), (2, 128, 16, 144, 2, 128, 256),
+                                                         (1, 2048, 512, 2560, 24, 128, 3072), (1, 5, 0, 5, 4, 64, 64)])
+def test_linear_qkv_epilogue(lib, Bs, rows, pos0, n_joint, H, dh, K, cta_group):
+    """EPI_QKV directly: bias -> per-head RMSNorm (two bf16 roundings) -> RoPE on interleaved pairs -> head-major scatter
+    into the joint [text;image] q/k/v at the right token position, against the reference's eager op sequence."""
+    g = torch.Generator(device="cuda").manual_seed(rows + H + dh + K)
+    M, D = Bs * rows, H * dh
+    A = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(3 * D, K, generator=g, device="cuda") * (K ** -0.5)).to(torch.bfloat16)
+    b = (torch.randn(3 * D, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    rq = (1 + 0.1 * torch.randn(dh, generator=g, device="cuda")).to(torch.bfloat16)
+    rk = (1 + 0.1 * torch.randn(dh, generator=g, device="cuda")).to(torch.bfloat16)
+    ang = torch.rand(n_joint, dh // 2, generator=g, device="cuda") * 6.28
+    ang[:, : dh // 16] = 0  # like axis 0 of FLUX's ids: never rotates
+    table = torch.stack([ang.cos(), ang.sin()], dim=-1).contiguous()  # [n_joint, dh/2, (cos, sin)] fp32
+    q = torch.full((Bs, H, n_joint, dh), 7.0, device="cuda", dtype=torch.bfloat16)
+    k, v = q.clone(), q.clone()
+    _chk(lib.tfx_op_linear_qkv(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), rq.data_ptr(), rk.data_ptr(), table.data_ptr(),
+                               q.data_ptr(), k.data_ptr(), v.data_ptr(), M, K, H, dh, rows, pos0, n_joint, cta_group, _stream()))
+    torch.cuda.synchronize()
+    pos = pos0 + torch.arange(M, device="cuda") % rows
+    cos = table[pos, :, 0].repeat_interleave(2, dim=-1)  # embeddings.py:868-869 repeat_interleave(2)
+    sin = table[pos, :, 1].repeat_interleave(2, dim=-1)
+    rq_, rk_, rv_ = _ref_qkv(A, W, b, rq, rk, cos, sin, H, dh)
+    for got, ref, nm in ((q, rq_, "q"), (k, rk_, "k"), (v, rv_, "v")):
+        got_rows = got[:, :, pos0:pos0 + rows].permute(0, 2, 1, 3).reshape(M, H, dh)
+        err = _rel(got_rows, ref)
+        assert err < 4e-3, (nm, err)  # accumulation order of the GEMM only; every rounding point is the reference's
+        # rows outside [pos0, pos0 + rows) belong to the other stream and must not be touched
+        untouched = torch.cat([got[:, :, :pos0], got[:, :, pos0 + rows:]], dim=2)
+        assert (untouched == 7.0).all(), nm
+    # exact index check: one-hot rows -> each token lands at its own position of its own head
+    A1 = torch.zeros_like(A)
+    A1[3 % M, 0] = 1.0
+    _chk(lib.tfx_op_linear_qkv(A1.data_ptr(), K, W.data_ptr(), torch.zeros_like(b).data_ptr(), rq.data_ptr(), rk.data_ptr(), table.data_ptr(),
+                               q.data_ptr(), k.data_ptr(), v.data_ptr(), M, K, H, dh, rows, pos0, n_joint, cta_group, _stream()))
+    torch.cuda.synchronize()
+    m = 3 % M
+    expect_v = W[2 * D:, 0].view(H, dh)
+    assert torch.equal(v[m // rows, :, pos0 + m % rows], expect_v)
+    other = v.clone()
+    other[m // rows, :, pos0 + m % rows] = 0
+    assert (other[:, :, pos0:pos0 + rows] == 0).all()
+
+
+@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
+@pytest.mark.parametrize("M,N,K", [(64, 64, 256), (4608, 64, 3072), (300, 16, 128)])
+def test_linear_euler_epilogue(lib, M, N, K, cta_group):
+    """EPI_EULER directly: noise_pred = bf16(A W^T + b) and, on the same store, latents' = bf16(latents + bf16(dt * v))
+    -- bit-exact against the reference scheduler's expression evaluated by torch on the kernel's own noise_pred."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * (K ** -0.5)).to(torch.bfloat16)
+    b = (torch.randn(N, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    x = torch.randn(M, N, generator=g, device="cuda").to(torch.bfloat16)
+    s0, s1 = torch.tensor(0.8125, device="cuda"), torch.tensor(0.7741, device="cuda")
+    dt = (s1 - s0).to(torch.bfloat16).float().reshape(1).contiguous()
+    v = torch.empty_like(x)
+    out = torch.empty_like(x)
+    _chk(lib.tfx_op_linear_euler(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), x.data_ptr(), dt.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                 M, N, K, cta_group, _stream()))
+    torch.cuda.synchronize()
+    assert _rel(v, A.float() @ W.float().T + b.float()) < 4e-3
+    ref = (x.to(torch.float32) + (s1 - s0) * v).to(torch.bfloat16)  # scheduling_flow_match_euler_discrete.py:322-330 on CUDA tensors
+    assert torch.equal(out, ref)
+    out2 = torch.empty_like(x)  # noise_pred output is optional
+    _chk(lib.tfx_op_linear_euler(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), x.data_ptr(), dt.data_ptr(), None, out2.data_ptr(),
+                                 M, N, K, cta_group, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out2, out)
+
+
 def test_linear_strided_a(lib):
     """A operand read out of a wider buffer (the [attn | mlp] concat tile): lda > K."""
     M, N, K, LD = 256, 256, 128, 640
@@ -190,6 +306,26 @@ def test_attention(lib, B, H, T, S, dh, q_tiles):
     ref = ref.transpose(1, 2).reshape(B, N, H * dh)
     err = _rel(out, ref)
     assert err < 8e-3, err
+
+
+@pytest.mark.parametrize("q_tiles", [26, 5], ids=["s3split_e2", "s3"])
+@pytest.mark.parametrize("B,H,T,S", [(1, 24, 512, 8192), (1, 6, 512, 12288), (1, 24, 512, 4096)])
+def test_attention_long_sequences(lib, B, H, T, S, q_tiles):
+    """BASELINE configs 4 / 5 and the 12 288-image-token reading of config 5 (N = 4608, 8704, 12 800), head_dim 128."""
+    dh = 128
+    g = torch.Generator(device="cuda").manual_seed(H * 100 + S)
+    N = T + S
+    q = torch.randn(B, H, N, dh, generator=g, device="cuda").to(torch.bfloat16)
+    k = torch.randn(B, H, N, dh, generator=g, device="cuda").to(torch.bfloat16)
+    v = torch.randn(B, H, N, dh, generator=g, device="cuda").to(torch.bfloat16)
+    out = _attention(lib, q, k, v, T, q_tiles)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    ref = ref.transpose(1, 2).reshape(B, N, H * dh)
+    err = _rel(out, ref)
+    lib16 = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, H * dh)
+    print(f"attention N={N} H={H}: ours-vs-fp32 {err:.3e}, torch bf16 SDPA-vs-fp32 {_rel(lib16, ref):.3e}")
+    assert err < 8e-3, err
+    assert err < 1.5 * _rel(lib16, ref) + 1e-4  # never further from fp32 than the library kernel the reference calls
 
 
 # ---------------------------------------------------------------------------------------------- pointwise kernels

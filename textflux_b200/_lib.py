@@ -35,6 +35,8 @@ SIGNATURES = {
     "tfx_set_schedule": (C.c_int, [_P, _P, _I32, _P, _P, _P]),
     "tfx_step_scheduled": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P]),
     "tfx_op_linear": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _P]),
+    "tfx_op_linear_qkv": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
+    "tfx_op_linear_euler": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "tfx_op_attention": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "tfx_op_ln_modulate": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _I64, _I64, _I64, _P]),
     "tfx_op_gemv": (C.c_int, [_P, _I32, _I32, _P, _P, _I64, _P, _I32, _P]),

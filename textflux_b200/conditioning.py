@@ -105,6 +105,9 @@ def pack_mask(mask: Tensor, height: int, width: int, vae_scale_factor: int = 8, 
     ch = vae_scale_factor * vae_scale_factor * 4
     if out is None:
         out = torch.empty(B, S, ch, device=mask.device, dtype=torch.bfloat16)
+    if out.dtype != torch.bfloat16 or not out.is_cuda or out.dim() != 3 or out.shape[0] != B or out.shape[1] != S or out.stride(2) != 1 \
+            or out.stride(0) != S * out.stride(1):
+        raise ValueError("out must be a bf16 CUDA tensor [B, S, ld] with contiguous tokens")
     with torch.cuda.device(mask.device):
         _lib.check(lib.tfx_op_pack_mask(mask.data_ptr(), int(mask.dtype == torch.float32), out.data_ptr(), out.stride(1), channel_offset,
                                         B, height, width, vae_scale_factor, _stream(mask)))

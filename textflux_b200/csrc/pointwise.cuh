@@ -16,10 +16,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0) applied to  bf16(bf16(t) * 1000)
 // (transformer_flux.py:1088-1090 then embeddings.py:27-78,1330-1334).  out [B,256] bf16 = [cos | sin].
 // in_is_f32: guidance arrives fp32, timestep arrives bf16.
-__global__ void timestep_embed_kernel(const void* __restrict__ t_in, int in_is_f32, int B, __nv_bfloat16* __restrict__ out) {
+// skip: optional device flag; the kernel does nothing when *skip >= 0 (modulation cache hit, see mod_cache_lookup_kernel)
+__global__ void timestep_embed_kernel(const void* __restrict__ t_in, int in_is_f32, int B, __nv_bfloat16* __restrict__ out,
+                                      const int* __restrict__ skip = nullptr) {
   const int b = blockIdx.x;
   const int k = threadIdx.x;  // 0..127
   if (b >= B || k >= 128) return;
+  if (skip && *skip >= 0) return;
   float t = in_is_f32 ? reinterpret_cast<const float*>(t_in)[b] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(t_in)[b]);
   t = bf16_round(bf16_round(t) * 1000.0f);
   const float exponent = (-9.210340371976184f * float(k)) / 128.0f;  // -ln(10000) * k / half_dim, fp32 like torch
@@ -38,8 +41,10 @@ constexpr int kGemvMaxB = 8;
 
 __global__ void __launch_bounds__(256) gemv_kernel(const __nv_bfloat16* __restrict__ x, int B, int K,
                                                   const __nv_bfloat16* __restrict__ W, const __nv_bfloat16* __restrict__ bias,
-                                                  long long N, __nv_bfloat16* out, int flags) {
+                                                  long long N, __nv_bfloat16* out, int flags,
+                                                  const int* __restrict__ skip = nullptr) {
   extern __shared__ __nv_bfloat16 xs[];  // [B][K], pre-activation applied (bf16 like the reference's silu output)
+  if (skip && *skip >= 0) return;  // modulation cache hit: the vectors this pass would produce are already stored
   for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
     float v = __bfloat162float(x[i]);
     if (flags & GEMV_PRE_SILU) v = bf16_round(silu(v));
@@ -250,5 +255,87 @@ __global__ void overshoot_step_kernel(const __nv_bfloat16* __restrict__ v, const
 }
 
 __global__ void set_float_kernel(float* dst, float value) { *dst = value; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Modulation cache of the drop-in path.  temb and all adaLN vectors depend only on (timestep, guidance, pooled)
+// (embeddings.py:1327-1339, normalization.py:167,200,363), and the unmodified pipeline hands the same triples over for
+// every image it samples with the same schedule and prompt template (pipeline_flux_fill.py:2082-2094).  The engine
+// therefore keeps the last `slots` results on the device, keyed on the exact input bits, and a captured step stays one
+// static graph: lookup -> (modulation kernels that return at once on a hit) -> commit.
+//   state[0] = slot that matches this step's inputs, or -1      state[1] = slot a miss is stored into
+//   state[2] = number of valid slots                             state[3] = hits so far (statistics)
+//   state[4] = round-robin replacement cursor
+struct ModCacheParams {
+  const __nv_bfloat16* t;       // [B] bf16
+  const float* g;               // [B] fp32 or null
+  const __nv_bfloat16* pooled;  // [B, P]
+  int B, P, slots;
+  uint16_t* key_t;              // [slots, B]
+  uint32_t* key_g;              // [slots, B]
+  uint16_t* key_p;              // [slots, B*P]
+  int* state;
+  __nv_bfloat16* mod;           // [B * mod_rows] the step's modulation vectors
+  __nv_bfloat16* table;         // [slots, B * mod_rows]
+  long long mod_elems;          // B * mod_rows
+};
+
+__global__ void __launch_bounds__(256) mod_cache_lookup_kernel(const ModCacheParams p) {
+  __shared__ int s_hit;
+  const uint16_t* t = reinterpret_cast<const uint16_t*>(p.t);
+  const uint32_t* g = reinterpret_cast<const uint32_t*>(p.g);
+  const uint16_t* pl = reinterpret_cast<const uint16_t*>(p.pooled);
+  const int valid = p.state[2];
+  if (threadIdx.x == 0) s_hit = -1;
+  __syncthreads();
+  for (int s = 0; s < valid; ++s) {
+    int ok = 1;
+    for (int i = threadIdx.x; i < p.B; i += blockDim.x)
+      ok &= (p.key_t[s * p.B + i] == t[i]) && (!g || p.key_g[s * p.B + i] == g[i]);
+    for (int i = threadIdx.x; ok && i < p.B * p.P; i += blockDim.x) ok &= p.key_p[(long long)s * p.B * p.P + i] == pl[i];
+    if (__syncthreads_and(ok)) {
+      if (threadIdx.x == 0) s_hit = s;
+      break;  // block-uniform
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int hit = s_hit;
+    p.state[0] = hit;
+    if (hit >= 0) {
+      p.state[3] += 1;
+    } else {
+      const int ins = p.state[4] % p.slots;  // round-robin replacement
+      p.state[1] = ins;
+      p.state[4] = ins + 1;
+      if (valid < p.slots) p.state[2] = valid + 1;
+    }
+  }
+}
+
+// hit: mod <- table[hit]; miss: table[insert] <- mod and the slot's keys <- this step's inputs
+__global__ void __launch_bounds__(256) mod_cache_commit_kernel(const ModCacheParams p) {
+  const int hit = p.state[0];
+  const long long n4 = p.mod_elems / 8;  // uint4 = 8 bf16; mod_rows is a multiple of 256
+  uint4* mod4 = reinterpret_cast<uint4*>(p.mod);
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  if (hit >= 0) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.table + (long long)hit * p.mod_elems);
+    for (long long i = tid; i < n4; i += nth) mod4[i] = src[i];
+    return;
+  }
+  const int ins = p.state[1];
+  uint4* dst = reinterpret_cast<uint4*>(p.table + (long long)ins * p.mod_elems);
+  for (long long i = tid; i < n4; i += nth) dst[i] = mod4[i];
+  if (blockIdx.x == 0) {
+    const uint16_t* t = reinterpret_cast<const uint16_t*>(p.t);
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(p.g);
+    const uint16_t* pl = reinterpret_cast<const uint16_t*>(p.pooled);
+    for (int i = threadIdx.x; i < p.B; i += blockDim.x) {
+      p.key_t[ins * p.B + i] = t[i];
+      p.key_g[ins * p.B + i] = g ? g[i] : 0u;
+    }
+    for (int i = threadIdx.x; i < p.B * p.P; i += blockDim.x) p.key_p[(long long)ins * p.B * p.P + i] = pl[i];
+  }
+}
 
 }  // namespace tfx

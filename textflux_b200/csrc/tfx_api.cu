@@ -500,7 +500,8 @@ void launch_ln_modulate(const LaunchCtx& c, const LnModParams& p) {
   ++*c.counter;
 }
 
-void launch_gemv(const LaunchCtx& c, const bf16* x, int B, int K, const bf16* W, const bf16* bias, long long N, bf16* out, int flags) {
+void launch_gemv(const LaunchCtx& c, const bf16* x, int B, int K, const bf16* W, const bf16* bias, long long N, bf16* out, int flags,
+                 const int* skip = nullptr) {
   std::string* err_ = c.err_;
   REQUIRE(K % 8 == 0, TFX_ERR_INVALID, "GEMV K=%d must be a multiple of 8", K);
   REQUIRE(B >= 1 && B <= kGemvMaxB, TFX_ERR_INVALID, "batch %d unsupported (1..%d)", B, kGemvMaxB);
@@ -510,7 +511,7 @@ void launch_gemv(const LaunchCtx& c, const bf16* x, int B, int K, const bf16* W,
   long long blocks = (N + 7) / 8;
   const long long cap = (long long)num_sms(c.device) * 8;
   if (blocks > cap) blocks = cap;
-  gemv_kernel<<<(unsigned)blocks, 256, smem, c.stream>>>(x, B, K, W, bias, N, out, flags);
+  gemv_kernel<<<(unsigned)blocks, 256, smem, c.stream>>>(x, B, K, W, bias, N, out, flags, skip);
   CUDA_TRY(cudaGetLastError());
   ++*c.counter;
 }
@@ -530,7 +531,7 @@ struct tfx_model {
   std::string* err_ = &err;
   long long launches = 0;
   long long graph_nodes = 0;
-  int gemm_cta_group = 1;
+  int gemm_cta_group = 2;  // 2-CTA 256x256 tiles: the configuration every published number was measured with
   int gemm_mcast = 0;  // 0: plain kernels; 2|4: pairs per cluster sharing A by TMA multicast
   int attn_q_tiles = 2;
   int attn_variant = 5;  // 1: v1 schedule (attn_q_tiles, attn_emu apply); 2, 3: QK-ahead schedules (measured slower);
@@ -539,6 +540,8 @@ struct tfx_model {
   int gemm_l2_hints = 0;  // bit 0: A (activation) loads evict_last, bit 1: B (weight) loads evict_first (option "gemm_l2_hints")
   int attn_emu = 2;  // column pairs per 8 whose exponentials run on the FMA pipe (packed polynomial) instead of MUFU:
                      // 2 measured best (+4..8 %), 0 = all MUFU
+  int mod_cache_slots = 64;  // drop-in path: modulation vectors of the last 64 distinct (t, guidance, pooled) triples stay
+                             // on the device (pointwise.cuh mod_cache_*); 0 = recompute every forward
   int use_graph = 1;
   int use_pdl = 1;  // programmatic dependent launch between the kernels of a step (measured -1.5 % step time)
   int profile = 0;
@@ -553,6 +556,7 @@ struct tfx_model {
 
   // per-request state
   int B = 0, S = 0, T = 0, N = 0;
+  int pB = 0, pS = 0, pT = 0;  // shape of the last tfx_prepare: an option that drops the workspace re-prepares lazily
   std::vector<void*> allocs;
   bf16 *hidden = nullptr, *nbuf = nullptr, *cat = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *mod = nullptr;
   bf16 *x_in = nullptr, *enc_in = nullptr, *pooled_in = nullptr, *t_in = nullptr, *ids_txt = nullptr, *ids_img = nullptr;
@@ -575,6 +579,9 @@ struct tfx_model {
   int sched_steps = 0;
   bf16 *sched_g = nullptr, *sched_pooled = nullptr, *sched_t = nullptr;
   std::vector<char> sched_pass_done;  // one flag per GEMV pass (kGemvMaxB rows of the table): passes run when first needed
+  // modulation cache of the unscheduled (drop-in) path
+  ModCacheParams mc;
+  bool mc_ready = false;
 
   const Weight& W(const std::string& name) {
     auto it = w.find(name);
@@ -611,6 +618,7 @@ struct tfx_model {
     if (sched_pooled) { cudaFree(sched_pooled); sched_pooled = nullptr; }
     if (sched_t) { cudaFree(sched_t); sched_t = nullptr; }
     sched_steps = 0;
+    mc_ready = false;
     B = S = T = N = 0;
   }
   template <typename Tp>
@@ -638,7 +646,9 @@ struct tfx_model {
   }
   void build_weight_maps();
   void prepare(int B_, int S_, int T_);
-  void enqueue_modulation(const LaunchCtx& c, const bf16* t_rows, const float* g_rows, const bf16* pooled_rows, int rows, bf16* mod_out);
+  void enqueue_modulation(const LaunchCtx& c, const bf16* t_rows, const float* g_rows, const bf16* pooled_rows, int rows, bf16* mod_out,
+                          const int* skip = nullptr);
+  void reset_modulation_caches();
   void enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_noise_pred, bool scheduled);
   void run(bool fused_euler, bool want_noise_pred, bool scheduled);
 };
@@ -651,6 +661,7 @@ void tfx_model::prepare(int B_, int S_, int T_) {
   if (B_ == B && S_ == S && T_ == T) return;
   free_workspace();
   B = B_; S = S_; T = T_; N = S + T;
+  pB = B_; pS = S_; pT = T_;
   const long long R = (long long)B * N;
   hidden = alloc<bf16>(R * D);
   nbuf = alloc<bf16>(R * D);
@@ -675,6 +686,21 @@ void tfx_model::prepare(int B_, int S_, int T_) {
   lat_out = alloc<bf16>((long long)B * S * cfg.out_channels);
   rope = alloc<float2>((long long)N * (dh / 2));
   CUDA_TRY(cudaMemset(cat, 0, R * 5 * D * sizeof(bf16)));
+  mc_ready = false;
+  if (mod_cache_slots > 0) {
+    const int P = cfg.pooled_projection_dim;
+    memset(&mc, 0, sizeof mc);
+    mc.t = t_in; mc.g = cfg.guidance_embeds ? g_in : nullptr; mc.pooled = pooled_in;
+    mc.B = B; mc.P = P; mc.slots = mod_cache_slots;
+    mc.key_t = alloc<uint16_t>((size_t)mod_cache_slots * B);
+    mc.key_g = alloc<uint32_t>((size_t)mod_cache_slots * B);
+    mc.key_p = alloc<uint16_t>((size_t)mod_cache_slots * B * P);
+    mc.state = alloc<int>(8);
+    mc.mod = mod; mc.mod_elems = (long long)B * mod_rows;
+    mc.table = alloc<bf16>((size_t)mod_cache_slots * B * mod_rows);
+    CUDA_TRY(cudaMemset(mc.state, 0, 8 * sizeof(int)));
+    mc_ready = true;
+  }
 
   const long long rt = (long long)B * T, ri = (long long)B * S;
   const long long row0[2] = {0, rt}, rows[2] = {rt, ri};
@@ -700,21 +726,27 @@ void tfx_model::prepare(int B_, int S_, int T_) {
 // temb = time_text_embed(timestep, guidance, pooled) (transformer_flux.py:1088-1098, embeddings.py:1327-1339) for `rows`
 // (<= 8) independent rows, then every adaLN `linear(silu(temb))` in one pass over the [mod_rows, D] matrix.
 void tfx_model::enqueue_modulation(const LaunchCtx& c, const bf16* t_rows, const float* g_rows, const bf16* pooled_rows, int rows,
-                                   bf16* mod_out) {
-  timestep_embed_kernel<<<rows, 128, 0, c.stream>>>(t_rows, 0, rows, tproj);
+                                   bf16* mod_out, const int* skip) {
+  timestep_embed_kernel<<<rows, 128, 0, c.stream>>>(t_rows, 0, rows, tproj, skip);
   ++*c.counter;
-  launch_gemv(c, tproj, rows, 256, W("t_embed.l1.w").ptr, W("t_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
-  launch_gemv(c, h1, rows, D, W("t_embed.l2.w").ptr, W("t_embed.l2.b").ptr, D, temb, 0);
+  launch_gemv(c, tproj, rows, 256, W("t_embed.l1.w").ptr, W("t_embed.l1.b").ptr, D, h1, GEMV_POST_SILU, skip);
+  launch_gemv(c, h1, rows, D, W("t_embed.l2.w").ptr, W("t_embed.l2.b").ptr, D, temb, 0, skip);
   if (cfg.guidance_embeds) {
-    timestep_embed_kernel<<<rows, 128, 0, c.stream>>>(g_rows, 1, rows, tproj);
+    timestep_embed_kernel<<<rows, 128, 0, c.stream>>>(g_rows, 1, rows, tproj, skip);
     ++*c.counter;
-    launch_gemv(c, tproj, rows, 256, W("g_embed.l1.w").ptr, W("g_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
-    launch_gemv(c, h1, rows, D, W("g_embed.l2.w").ptr, W("g_embed.l2.b").ptr, D, temb, GEMV_ADD_TO_OUT);
+    launch_gemv(c, tproj, rows, 256, W("g_embed.l1.w").ptr, W("g_embed.l1.b").ptr, D, h1, GEMV_POST_SILU, skip);
+    launch_gemv(c, h1, rows, D, W("g_embed.l2.w").ptr, W("g_embed.l2.b").ptr, D, temb, GEMV_ADD_TO_OUT, skip);
   }
-  launch_gemv(c, pooled_rows, rows, cfg.pooled_projection_dim, W("p_embed.l1.w").ptr, W("p_embed.l1.b").ptr, D, h1, GEMV_POST_SILU);
-  launch_gemv(c, h1, rows, D, W("p_embed.l2.w").ptr, W("p_embed.l2.b").ptr, D, temb, GEMV_ADD_TO_OUT);
+  launch_gemv(c, pooled_rows, rows, cfg.pooled_projection_dim, W("p_embed.l1.w").ptr, W("p_embed.l1.b").ptr, D, h1, GEMV_POST_SILU, skip);
+  launch_gemv(c, h1, rows, D, W("p_embed.l2.w").ptr, W("p_embed.l2.b").ptr, D, temb, GEMV_ADD_TO_OUT, skip);
   CUDA_TRY(cudaGetLastError());
-  launch_gemv(c, temb, rows, D, W("mod.w").ptr, W("mod.b").ptr, mod_rows, mod_out, GEMV_PRE_SILU);
+  launch_gemv(c, temb, rows, D, W("mod.w").ptr, W("mod.b").ptr, mod_rows, mod_out, GEMV_PRE_SILU, skip);
+}
+
+// Weights changed in place (LoRA hot-swap): nothing cached from the old weights may be served again.
+void tfx_model::reset_modulation_caches() {
+  if (mc_ready) CUDA_TRY(cudaMemsetAsync(mc.state, 0, 8 * sizeof(int), stream));
+  std::fill(sched_pass_done.begin(), sched_pass_done.end(), 0);
 }
 
 void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_noise_pred, bool scheduled) {
@@ -738,7 +770,23 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
   }
   // --- temb + every adaLN `linear(silu(temb))` of the step; with a schedule set they were computed for all steps at
   //     once (tfx_set_schedule) and this step's rows were copied into `mod` before the launch
-  if (!scheduled) enqueue_modulation(c, t_in, g_in, pooled_in, B, mod);
+  if (!scheduled) {
+    // drop-in path: the pipeline passes (t, guidance, pooled) per call; a triple seen before (the same schedule step of an
+    // earlier image) is served from the device-side cache, a new one is computed and stored -- one static graph either way
+    const bool cached = mc_ready && mod_cache_slots > 0;
+    if (cached) {
+      ProfScope ps(c, KF_MISC);
+      mod_cache_lookup_kernel<<<1, 256, 0, c.stream>>>(mc);
+      ++*c.counter;
+    }
+    enqueue_modulation(c, t_in, g_in, pooled_in, B, mod, cached ? mc.state : nullptr);
+    if (cached) {
+      ProfScope ps(c, KF_MISC);
+      mod_cache_commit_kernel<<<num_sms(device) * 2, 256, 0, c.stream>>>(mc);
+      CUDA_TRY(cudaGetLastError());
+      ++*c.counter;
+    }
+  }
 
   auto base_params = [&](int Nn, int Kk) {
     GemmParams p;
@@ -1011,11 +1059,16 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
     REQUIRE(value == 0 || (value >= 2 && value <= 4), TFX_ERR_INVALID, "attn_emu must be 0, 2, 3 or 4");
     h->attn_emu = (int)value;
   } else if (k == "gemm_narrow_tiles") {
-    h->gemm_narrow_tiles = value != 0;
-    h->free_workspace();  // B-side descriptors depend on the tile width: the next tfx_prepare rebuilds them
+    h->gemm_narrow_tiles = value != 0;  // weight-side descriptors are keyed by tile width: nothing to rebuild
   } else if (k == "gemm_l2_hints") {
     REQUIRE(value >= 0 && value <= 3, TFX_ERR_INVALID, "gemm_l2_hints must be 0..3");
     h->gemm_l2_hints = (int)value;
+  } else if (k == "mod_cache_slots") {
+    REQUIRE(value >= 0 && value <= 4096, TFX_ERR_INVALID, "mod_cache_slots must be 0..4096");
+    h->mod_cache_slots = (int)value;
+    h->free_workspace();  // the cache is part of the workspace: the next tfx_prepare sizes it
+  } else if (k == "mod_cache_reset") {
+    h->reset_modulation_caches();
   } else if (k == "use_graph") {
     h->use_graph = value != 0;
   } else if (k == "use_pdl") {
@@ -1036,6 +1089,14 @@ int tfx_get_counter(tfx_handle h, const char* key, int64_t* value) {
   std::string k(key);
   if (k == "launches") *value = h->launches;
   else if (k == "graph_nodes") *value = h->graph_nodes;
+  else if (k == "mod_cache_hits" || k == "mod_cache_valid") {
+    int st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (h->mc_ready) {
+      CUDA_TRY(cudaStreamSynchronize(h->stream));
+      CUDA_TRY(cudaMemcpy(st, h->mc.state, sizeof st, cudaMemcpyDeviceToHost));
+    }
+    *value = (k == "mod_cache_hits") ? st[3] : st[2];
+  }
   else if (k.compare(0, 8, "prof_us_") == 0 || k.compare(0, 7, "prof_n_") == 0) {
     const bool is_us = k.compare(0, 8, "prof_us_") == 0;
     const std::string fam = k.substr(is_us ? 8 : 7);
@@ -1112,6 +1173,7 @@ int tfx_prepare(tfx_handle h, int32_t B, int32_t S, int32_t T) {
 
 static void stage_common(tfx_model* h, std::string* err_, const void* enc, const void* pooled, const void* t, const void* g,
                          const void* img_ids, const void* txt_ids, cudaStream_t user, bool scheduled = false) {
+  if (h->B == 0 && h->pB > 0) h->prepare(h->pB, h->pS, h->pT);  // an option dropped the workspace since
   REQUIRE(h->B > 0, TFX_ERR_STATE, "tfx_prepare has not been called");
   REQUIRE(enc && img_ids && txt_ids && (scheduled || (pooled && t)), TFX_ERR_INVALID, "null input pointer");
   REQUIRE(scheduled || !h->cfg.guidance_embeds || g, TFX_ERR_INVALID, "guidance is required when guidance_embeds is set");
@@ -1180,6 +1242,8 @@ int tfx_set_schedule(tfx_handle h, const void* timesteps_bf16, int32_t n_steps, 
                      void* stream) {
   API_BEGIN(h)
   REQUIRE(h && timesteps_bf16 && pooled && n_steps > 0, TFX_ERR_INVALID, "bad argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->B == 0 && h->pB > 0) h->prepare(h->pB, h->pS, h->pT);
   REQUIRE(h->B > 0, TFX_ERR_STATE, "tfx_prepare has not been called");
   REQUIRE(!h->cfg.guidance_embeds || guidance_f32, TFX_ERR_INVALID, "guidance is required when guidance_embeds is set");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -1325,6 +1389,69 @@ int tfx_op_linear(const void* A, int64_t lda, const void* Wt, const void* bias, 
     LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
     if (pn) launch_gemm_mc(c, pn, bn, ma, ma, mb, mb, p);
     else launch_gemm(c, cta_group, bn, ma, ma, mb, mb, p);
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+int tfx_op_linear_qkv(const void* A, int64_t lda, const void* Wt, const void* bias, const void* rms_q, const void* rms_k,
+                      const void* rope_f32, void* q, void* k, void* v, int32_t M, int32_t K, int32_t H, int32_t head_dim,
+                      int32_t rows_per_sample, int32_t pos_offset, int32_t n_joint, int32_t cta_group, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(A && Wt && bias && rms_q && rms_k && rope_f32 && q && k && v, TFX_ERR_INVALID, "null argument");
+    REQUIRE(cta_group == 1 || cta_group == 2, TFX_ERR_INVALID, "cta_group must be 1 or 2");
+    REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "head_dim %d unsupported (64 or 128)", head_dim);
+    REQUIRE((H * head_dim) % 256 == 0, TFX_ERR_INVALID, "H * head_dim = %d must be a multiple of 256", H * head_dim);
+    REQUIRE(rows_per_sample > 0 && pos_offset >= 0 && pos_offset + rows_per_sample <= n_joint, TFX_ERR_INVALID,
+            "rows_per_sample %d at offset %d does not fit n_joint %d", rows_per_sample, pos_offset, n_joint);
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    configure_kernels(err_);
+    if (M == 0) return TFX_OK;
+    const int D = H * head_dim, N = 3 * D;
+    CUtensorMap ma = make_map_2d(err_, A, M, K, lda, 128);
+    CUtensorMap mb = make_map_2d(err_, Wt, N, K, K, 256 / cta_group);
+    GemmParams p;
+    memset(&p, 0, sizeof p);
+    p.N = N; p.K = K; p.num_groups = 1; p.n_split = N; p.mode0 = EPI_QKV; p.mode1 = EPI_QKV;
+    p.D = D; p.head_dim = head_dim; p.num_heads = H; p.n_joint = n_joint;
+    p.q = reinterpret_cast<bf16*>(q); p.k = reinterpret_cast<bf16*>(k); p.v = reinterpret_cast<bf16*>(v);
+    p.rope = reinterpret_cast<const float2*>(rope_f32); p.rms_eps = 1e-6f;
+    p.g[0].M = M; p.g[0].rows_per_sample = rows_per_sample; p.g[0].pos_offset = pos_offset;
+    p.g[0].bias = reinterpret_cast<const bf16*>(bias);
+    p.g[0].rms_q = reinterpret_cast<const bf16*>(rms_q); p.g[0].rms_k = reinterpret_cast<const bf16*>(rms_k);
+    LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
+    launch_gemm(c, cta_group, 256, ma, ma, mb, mb, p);
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+int tfx_op_linear_euler(const void* A, int64_t lda, const void* Wt, const void* bias, const void* latents_in, const void* dt_f32_dev,
+                        void* noise_pred_out, void* latents_out, int32_t M, int32_t N, int32_t K, int32_t cta_group, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(A && Wt && bias && latents_in && dt_f32_dev && latents_out, TFX_ERR_INVALID, "null argument");
+    REQUIRE(cta_group == 1 || cta_group == 2, TFX_ERR_INVALID, "cta_group must be 1 or 2");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    configure_kernels(err_);
+    if (M == 0) return TFX_OK;
+    CUtensorMap ma = make_map_2d(err_, A, M, K, lda, 128);
+    CUtensorMap mb = make_map_2d(err_, Wt, N, K, K, 256 / cta_group);
+    GemmParams p;
+    memset(&p, 0, sizeof p);
+    p.N = N; p.K = K; p.num_groups = 1; p.n_split = N; p.mode0 = EPI_EULER; p.mode1 = EPI_EULER;
+    p.dt_ptr = reinterpret_cast<const float*>(dt_f32_dev);
+    p.g[0].M = M; p.g[0].rows_per_sample = M; p.g[0].bias = reinterpret_cast<const bf16*>(bias);
+    p.g[0].out = reinterpret_cast<bf16*>(noise_pred_out); p.g[0].ldo = N;
+    p.g[0].res = reinterpret_cast<const bf16*>(latents_in); p.g[0].ldr = N;
+    p.g[0].out2 = reinterpret_cast<bf16*>(latents_out);
+    LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
+    launch_gemm(c, cta_group, 256, ma, ma, mb, mb, p);
   } catch (const Fail& f) {
     return f.code;
   }

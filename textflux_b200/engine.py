@@ -68,7 +68,9 @@ class B200FluxTransformer(torch.nn.Module):
 
     def __init__(self, config, get: Callable[[str], Tensor], device: Union[str, torch.device] = "cuda",
                  gemm_cta_group: Optional[int] = None, attn_q_tiles: Optional[int] = None, use_graph: bool = True,
-                 gemm_mcast: Optional[int] = None):
+                 gemm_mcast: Optional[int] = None, lora_modules=None):
+        """`lora_modules`: reference module names whose weights `get` returns with an adapter already folded in (a
+        `fold_lora` getter); recorded so that a later `load_lora_weights` / `unload_lora_weights` restores them."""
         super().__init__()
         self._lib = _lib.load()
         dev = torch.device(device)
@@ -96,7 +98,8 @@ class B200FluxTransformer(torch.nn.Module):
         if attn_q_tiles is not None:
             self.set_option("attn_q_tiles", attn_q_tiles)
         self._shape: Optional[Tuple[int, int, int]] = None
-        self._lora_modules: set = set()
+        folded = getattr(get, "lora_modules", None) if lora_modules is None else lora_modules
+        self._lora_modules: set = set(folded or ())
         self.set_option("use_graph", int(use_graph))
         if gemm_mcast is not None:
             self.set_option("gemm_mcast", gemm_mcast)
@@ -104,9 +107,35 @@ class B200FluxTransformer(torch.nn.Module):
     # ---- construction helpers -------------------------------------------------------------------------------
     @classmethod
     def from_reference(cls, module: torch.nn.Module, device="cuda", **kw) -> "B200FluxTransformer":
-        """`module` is a loaded reference FluxTransformer2DModel (weights + `.config`); it can be freed afterwards."""
+        """`module` is a loaded reference FluxTransformer2DModel (weights + `.config`); it can be freed afterwards.
+        A module carrying PEFT adapters (FluxFillPipeline.load_lora_weights -> load_lora_into_transformer,
+        loaders/lora_pipeline.py:1745-1820, as run_inference_lora.py:52-65 / demo_beta.py leave it) has its active
+        adapters folded into the packed weights: W + sum_a scaling[a] * B_a @ A_a in fp32."""
         sd = module.state_dict()
-        return cls(module.config, sd.__getitem__, device=device, **kw)
+        peft = _peft_layers(module)
+        if not peft and any(".base_layer." in k or ".lora_A." in k for k in sd):
+            raise ValueError("textflux_b200: the transformer's state dict has PEFT keys (…base_layer.weight / …lora_A.<adapter>"
+                             ".weight) but no PEFT layer objects were found to read `scaling` from; fold the adapter "
+                             "with textflux_b200.fold_lora(...) and build the engine from that getter instead")
+        if not peft:
+            return cls(module.config, sd.__getitem__, device=device, **kw)
+
+        def get(name: str) -> Tensor:
+            mod, _, leaf = name.rpartition(".")
+            if mod not in peft:
+                return sd[name]
+            layer = peft[mod]
+            base = sd[f"{mod}.base_layer.{leaf}"]
+            if leaf != "weight":
+                return base
+            w = base.to(torch.float32)
+            for a in _active_adapters(layer):
+                A = sd[f"{mod}.lora_A.{a}.weight"].to(device=w.device, dtype=torch.float32)
+                Bm = sd[f"{mod}.lora_B.{a}.weight"].to(device=w.device, dtype=torch.float32)
+                w = w + float(layer.scaling[a]) * (Bm @ A)
+            return w.to(base.dtype)
+
+        return cls(module.config, get, device=device, lora_modules=set(peft), **kw)
 
     @classmethod
     def from_state_dict(cls, config, state_dict: Dict[str, Tensor], device="cuda", **kw) -> "B200FluxTransformer":
@@ -125,6 +154,7 @@ class B200FluxTransformer(torch.nn.Module):
             repack_modules(SimpleNamespace(**self.config), fold_lora(get_base, lora, scale=scale), self._weights, mods)
             torch.cuda.current_stream(self._dev).synchronize()
         self._lora_modules = set(lora_modules(lora))
+        self.set_option("mod_cache_reset", 1)  # modulation vectors cached from the old weights must not be served again
 
     def unload_lora_weights(self, get_base: Callable[[str], Tensor]) -> None:
         """Restore the base weights of every module the current adapter touched."""
@@ -133,6 +163,7 @@ class B200FluxTransformer(torch.nn.Module):
             repack_modules(SimpleNamespace(**self.config), get_base, self._weights, self._lora_modules)
             torch.cuda.current_stream(self._dev).synchronize()
         self._lora_modules = set()
+        self.set_option("mod_cache_reset", 1)
 
     # ---- what DiffusionPipeline reads -------------------------------------------------------------------------
     @property
@@ -156,7 +187,7 @@ class B200FluxTransformer(torch.nn.Module):
 
     def set_option(self, key: str, value: int) -> None:
         _lib.check(self._lib.tfx_set_option(self._h, key.encode(), int(value)), self._h)
-        if key == "gemm_mcast":
+        if key in ("gemm_mcast", "mod_cache_slots"):
             self._shape = None  # the library dropped its workspace; re-run tfx_prepare on the next call
 
     def counter(self, key: str) -> int:
@@ -188,7 +219,12 @@ class B200FluxTransformer(torch.nn.Module):
     def _ids(self, ids: Tensor, name: str, n: int) -> Tensor:
         if ids.ndim == 3:  # deprecated batched ids (transformer_flux.py:1100-1113)
             ids = ids[0]
-        return self._bf16(ids, name, (n, 3))
+        out = self._bf16(ids, name, (n, 3))
+        if ids.dtype != torch.bfloat16 and not torch.equal(out.to(ids.dtype), ids.to(self._dev)):
+            # the engine's RoPE table takes bf16 ids, which is what the pipeline passes (pipeline_flux_fill.py:1728-1739
+            # builds them in the latents' dtype); fp32 ids above 256 (> 4096 px) would be rounded
+            raise ValueError(f"textflux_b200: `{name}` holds positions that bf16 cannot represent exactly")
+        return out
 
     # ---- FluxTransformer2DModel.forward (transformer_flux.py:1028-1212) -------------------------------------------
     @torch.no_grad()
@@ -295,10 +331,19 @@ class B200FluxTransformer(torch.nn.Module):
     def denoise(self, latents: Tensor, cond: Tensor, prompt_embeds: Tensor, pooled_prompt_embeds: Tensor,
                 txt_ids: Tensor, img_ids: Tensor, guidance_scale: float, num_inference_steps: int,
                 scheduler: Optional["B200FlowMatchEulerScheduler"] = None,
-                callback: Optional[Callable[[int, Tensor], None]] = None, precompute_modulation: bool = True) -> Tensor:
+                callback: Optional[Callable[[int, Tensor], None]] = None, precompute_modulation: bool = True,
+                callback_on_step_end: Optional[Callable] = None,
+                callback_on_step_end_tensor_inputs: Tuple[str, ...] = ("latents",)) -> Tensor:
         """The whole loop of FluxFillPipeline.__call__ (pipeline_flux_fill.py:2049-2119): schedule, then one fused
-        step per timestep.  Returns the final packed latents."""
+        step per timestep.  Returns the final packed latents.
+
+        `callback_on_step_end(self, i, t, callback_kwargs) -> dict` follows the pipeline's contract (:2105-2112): it is
+        handed the tensors named in `callback_on_step_end_tensor_inputs` ("latents", "prompt_embeds") and whatever it
+        returns under those names REPLACES them for the following steps.  Setting `self.interrupt = True` (from the
+        callback or another thread) skips the remaining steps like :2078-2079.  `callback(i, latents)` is the
+        observe-only short form."""
         sch = scheduler or B200FlowMatchEulerScheduler()
+        self.interrupt = False
         B, S = latents.shape[0], latents.shape[1]
         T = prompt_embeds.shape[1]
         mu = calculate_shift(S, sch.config.base_image_seq_len, sch.config.max_image_seq_len, sch.config.base_shift,
@@ -312,11 +357,22 @@ class B200FluxTransformer(torch.nn.Module):
         if precompute_modulation:
             self.set_schedule(ts, guidance, pooled_prompt_embeds, S, T)
         for i in range(len(sch.timesteps)):
+            if self.interrupt:
+                continue
             if precompute_modulation:
                 latents = self.step_scheduled(i, latents, cond, prompt_embeds, img_ids, txt_ids, sig[i], sig[i + 1])
             else:
                 latents = self.step(latents, cond, prompt_embeds, pooled_prompt_embeds, ts[i], guidance, img_ids, txt_ids,
                                     sig[i], sig[i + 1])
+            if callback_on_step_end is not None:
+                have = {"latents": latents, "prompt_embeds": prompt_embeds}
+                unknown = [k for k in callback_on_step_end_tensor_inputs if k not in have]
+                if unknown:
+                    raise ValueError(f"`callback_on_step_end_tensor_inputs` has to be in ['latents', 'prompt_embeds'], "
+                                     f"but found {unknown}")
+                outs = callback_on_step_end(self, i, sch.timesteps[i], {k: have[k] for k in callback_on_step_end_tensor_inputs})
+                latents = outs.pop("latents", latents)
+                prompt_embeds = outs.pop("prompt_embeds", prompt_embeds)
             if callback is not None:
                 callback(i, latents)
         return latents
@@ -362,6 +418,13 @@ class B200FlowMatchEulerScheduler:
     @classmethod
     def from_config(cls, config) -> "B200FlowMatchEulerScheduler":
         get = (lambda k, d: config.get(k, d)) if isinstance(config, dict) else (lambda k, d: getattr(config, k, d))
+        unsupported = [k for k in ("use_karras_sigmas", "use_exponential_sigmas", "use_beta_sigmas", "invert_sigmas")
+                       if get(k, False)]
+        if get("shift_terminal", None):
+            unsupported.append("shift_terminal")
+        if unsupported:
+            raise ValueError(f"textflux_b200: scheduler config sets {unsupported}, which the FLUX-Fill path never does and "
+                             f"this scheduler does not implement; keep the reference scheduler for that configuration")
         return cls(get("num_train_timesteps", 1000), get("shift", 1.0), get("use_dynamic_shifting", True),
                    get("base_shift", 0.5), get("max_shift", 1.15), get("base_image_seq_len", 256),
                    get("max_image_seq_len", 4096))
@@ -431,6 +494,10 @@ class B200FlowMatchEulerScheduler:
             raise RuntimeError("textflux_b200: scheduler.step runs on CUDA tensors only (no CPU path)")
         if model_output.dtype != torch.bfloat16 or model_output.shape != sample.shape:
             raise ValueError("textflux_b200: scheduler.step expects bf16 model_output with sample's shape")
+        if sample.dtype != torch.bfloat16:
+            # the reference upcasts `sample` to fp32 and casts the result back to model_output.dtype (:322-330); with an fp32
+            # sample that is a different rounding than this bf16 kernel implements
+            raise ValueError("textflux_b200: scheduler.step expects a bf16 sample (the FLUX-Fill pipeline's latents dtype)")
         sigma, sigma_next = self.sigmas_cpu[self._step_index], self.sigmas_cpu[self._step_index + 1]
         v = model_output.contiguous()
         x = sample.to(torch.bfloat16).contiguous()
@@ -548,6 +615,29 @@ class B200StochasticRFOvershotScheduler(B200FlowMatchEulerScheduler):
         if not return_dict:
             return (prev, x1)
         return SimpleNamespace(prev_sample=prev, predicted_x1=x1)
+
+
+def _peft_layers(module: torch.nn.Module) -> Dict[str, torch.nn.Module]:
+    """{module name: PEFT LoRA layer} for every wrapped Linear of `module` (peft.tuners.lora.layer.Linear keeps the
+    original as `.base_layer` and the adapters in `.lora_A` / `.lora_B` ModuleDicts with `.scaling[adapter]`)."""
+    out = {}
+    for name, m in module.named_modules():
+        if hasattr(m, "base_layer") and hasattr(m, "lora_A") and hasattr(m, "lora_B") and hasattr(m, "scaling"):
+            out[name] = m
+    return out
+
+
+def _active_adapters(layer) -> List[str]:
+    if getattr(layer, "merged", False) or getattr(layer, "disable_adapters", False):
+        return []
+    act = getattr(layer, "active_adapters", None)
+    if act is None:
+        act = getattr(layer, "active_adapter", None)
+    if act is None:
+        act = list(layer.lora_A.keys())
+    if isinstance(act, str):
+        act = [act]
+    return [a for a in act if a in layer.lora_A]
 
 
 def attach(pipe, **engine_kw):

@@ -13,7 +13,7 @@ that each fused kernel streams one matrix:
                          norm.linear (3D); norm_out.linear (2D)                           (normalization.py:148,187,353)
     t_embed / g_embed / p_embed .l1/.l2     time_text_embed MLPs                          (embeddings.py:1318-1339)
 
-Row re-ordering only: every value is copied bit-exactly (tests/test_packer.py).  LoRA adapters are folded at pack
+Row re-ordering only: every value is copied bit-exactly (tests/test_host_cpu.py::test_packer_is_a_bit_exact_row_regrouping).  LoRA adapters are folded at pack
 time, W <- W + (alpha/r) * B @ A in fp32 (loaders/lora_pipeline.py:1618-1743 file format), see fold_lora().
 """
 from __future__ import annotations
@@ -192,6 +192,7 @@ def fold_lora(get: Callable[[str], Tensor], lora: Dict[str, Tensor], scale: floa
             w = (w.to(torch.float32) + (scale * alpha / r) * (Bm @ A)).to(w.dtype)
         return w
 
+    wrapped.lora_modules = set(mods)  # B200FluxTransformer records them so a later swap / unload restores these modules
     return wrapped
 
 
