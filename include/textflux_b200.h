@@ -49,7 +49,7 @@ int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
 void tfx_destroy(tfx_handle h);
 /* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
 const char* tfx_last_error(tfx_handle h);
-/* "gemm_narrow_tiles" (0|1: allow 224-wide GEMM tiles against wave quantisation), "gemm_l2_hints" (0..3: bit 0 activations evict_last, bit 1 weights evict_first in the GEMM's TMA loads), "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (1..7; 5 = schedule 3 split-P, 6 = schedule 3 row-split, 7 = CTA-pair schedule), "attn_q_tiles" (1|2), "attn_emu" (0|2|3|4), "use_graph" (0|1), "mod_cache_slots" (0..4096: device-side cache of modulation vectors keyed on the (timestep, guidance, pooled) bits tfx_forward / tfx_step receive; 0 = recompute every call), "mod_cache_reset" (drop every cached modulation vector: call after rewriting weights in place), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
+/* "gemm_narrow_tiles" (0|1: allow 224-wide GEMM tiles against wave quantisation), "gemm_l2_hints" (0..3: bit 0 activations evict_last, bit 1 weights evict_first in the GEMM's TMA loads), "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (0 = per shape, schedule 3 or 5 (default); 4 | 5 = schedule 3 whole-P / split-P, 8 = schedule 4 stream, 9 = schedule 5 persistent stream), "attn_emu" (0|2|3|4), "use_graph" (0|1), "mod_cache_slots" (0..4096: device-side cache of modulation vectors keyed on the (timestep, guidance, pooled) bits tfx_forward / tfx_step receive; 0 = recompute every call), "mod_cache_reset" (drop every cached modulation vector: call after rewriting weights in place), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
  * pair per kernel, summed per family; resets the sums) */
 int tfx_set_option(tfx_handle h, const char* key, int64_t value);
 /* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step;
@@ -125,17 +125,20 @@ int tfx_op_linear_qkv(const void* A, int64_t lda, const void* W, const void* bia
  * dt_f32_dev a DEVICE scalar holding float(bf16(sigma_next - sigma)). */
 int tfx_op_linear_euler(const void* A, int64_t lda, const void* W, const void* bias, const void* latents_in, const void* dt_f32_dev,
                         void* noise_pred_out, void* latents_out, int32_t M, int32_t N, int32_t K, int32_t cta_group, void* stream);
-/* q,k,v [B,H,N,dh] -> out rows in the engine's [B*T text rows ; B*S image rows] order, row stride ld_out;
- * q_tiles = 3 | 4: QK-ahead schedule (2 query tiles x 64-key tiles | 1 query tile x 128-key tiles);
- * q_tiles % 10 = 5 | 6 | 7: schedule 3 (attention3.cuh; 6 = P handed over in two halves, 7 = two threads per score
- * row), + 10 * emu, + 100 to trace;  q_tiles % 10 = 8: CTA-pair schedule (attention_pair.cuh, head_dim 128), + 10 * emu;
- * else v1 schedule with q_tiles = tiles + 10 * emu
- * (emu = exponentials per 8 evaluated by the FMA-pipe polynomial: 0, 2, 3, 4) */
+/* q,k,v [B,H,N,dh] -> out rows in the engine's [B*T text rows ; B*S image rows] order, row stride ld_out.
+ * schedule = code % 10: 5 | 6 = schedule 3 (attention3.cuh: one CTA per 256 query rows of a head; 6 hands P to the tensor
+ * pipe in two halves), 9 = schedule 4 (attention4.cuh: schedule 3/6 plus the last partial wave cut into KV shares),
+ * 7 = schedule 5 (attention5.cuh: one persistent CTA per SM, items overlapped, remainder cut into KV shares); + 10 * emu (exponentials per 8 column pairs evaluated by the FMA-pipe polynomial: 0, 2, 3, 4);
+ * + 100 with schedule 6 records clock stamps (tfx_debug_set_attention_trace) */
 int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int64_t ld_out, int32_t B, int32_t H,
-                     int32_t T, int32_t S, int32_t head_dim, int32_t q_tiles, void* stream);
+                     int32_t T, int32_t S, int32_t head_dim, int32_t schedule_code, void* stream);
 /* debug: device buffer [n_kv_tiles * 2 * 8] int64 receiving clock64 stamps of CTA (0,0,0) of the schedule-3 attention
- * kernel when tfx_op_attention is called with q_tiles >= 100 (tools/attn_trace.py); NULL switches it off */
+ * kernel when tfx_op_attention is called with code >= 100 (tools/attn_trace.py); NULL switches it off */
 int tfx_debug_set_attention_trace(void* dev_ptr);
+/* debug: device buffer [num CTAs * 8] int64 receiving per-CTA globaltimer stamps (entry, set-up done, Q + first K landed,
+ * first scores seen, last P handed over, last PV retired, output stored, SM id) of the same trace build
+ * (tools/attn_timeline.py); NULL switches it off */
+int tfx_debug_set_attention_cta_trace(void* dev_ptr);
 /* y = LN(x)*(1+scale)+shift per row; mod [B, mod_stride]; rows = B*rows_per_sample */
 int tfx_op_ln_modulate(const void* x, void* y, int32_t rows, int32_t D, int32_t rows_per_sample, const void* mod,
                        int64_t mod_stride, int64_t shift_off, int64_t scale_off, void* stream);

@@ -31,15 +31,15 @@ def _cuda(d):
     return {k: v.cuda() for k, v in d.items()}
 
 
-@pytest.mark.parametrize("cta_group,q_tiles,graph,mcast", [(1, 1, False, 0), (1, 2, True, 0), (2, 2, True, 0), (2, 1, False, 0),
-                                                           (2, 2, True, 2), (2, 2, False, 4)])
-def test_tiny_forward_vs_reference_golden(golden, cta_group, q_tiles, graph, mcast):
+@pytest.mark.parametrize("cta_group,attn,graph,mcast", [(1, 4, False, 0), (1, 5, True, 0), (2, 8, True, 0), (2, 5, False, 0),
+                                                        (2, 9, True, 2), (2, 9, False, 4), (1, 9, True, 0)])
+def test_tiny_forward_vs_reference_golden(golden, cta_group, attn, graph, mcast):
     g = golden("tiny_forward.pt")
     cfg = fo.FluxConfig(**g["config"])
     sd = fo.init_state_dict(cfg, seed=g["weight_seed"])
-    eng = _engine(cfg, sd, gemm_cta_group=cta_group, attn_q_tiles=q_tiles, use_graph=graph, gemm_mcast=mcast)
-    eng.set_option("attn_variant", 1 if mcast == 0 and cta_group == 1 else (2 if graph else 3))  # all attention schedules
-    eng.set_option("use_pdl", 0 if (cta_group == 2 and q_tiles == 1) else 1)  # with and without programmatic dependent launch
+    eng = _engine(cfg, sd, gemm_cta_group=cta_group, use_graph=graph, gemm_mcast=mcast)
+    eng.set_option("attn_variant", attn)  # all attention schedules
+    eng.set_option("use_pdl", 0 if (cta_group == 2 and attn == 5) else 1)  # with and without programmatic dependent launch
     inp = _cuda(g["inputs"])
     hs = torch.cat([inp["latents"], inp["cond"]], dim=2)
     for _ in range(2):  # second call replays the captured graph
@@ -51,7 +51,7 @@ def test_tiny_forward_vs_reference_golden(golden, cta_group, q_tiles, graph, mca
         ref16, ref32 = g["sample"], g["sample_fp32"]
         base = _rel(ref16, ref32)
         e16, e32 = _rel(out, ref16), _rel(out, ref32)
-        print(f"tiny forward cta_group={cta_group} q_tiles={q_tiles}: ref16-vs-fp32 {base:.3e} engine-vs-ref16 {e16:.3e} "
+        print(f"tiny forward cta_group={cta_group} attn_variant={attn}: ref16-vs-fp32 {base:.3e} engine-vs-ref16 {e16:.3e} "
               f"engine-vs-fp32 {e32:.3e} cosdist {_cosdist(out, ref16):.2e}")
         assert torch.isfinite(out.float()).all()
         assert e16 <= 2.0 * base, (e16, base)
@@ -202,7 +202,14 @@ def test_full_size_12b_properties():
     assert torch.isfinite(v.float()).all() and v.shape == (1, S, 64)
     assert torch.equal(v, fwd(one, inp["img_ids"], hs[one]))                                   # deterministic (graph replay)
     both = fwd(slice(0, 2), inp["img_ids"], hs)
-    assert torch.equal(both[0], v[0])                                                           # batch rows independent
+    # batch rows independent.  The default attention schedule may cut the last partial wave of (head, query-pair) units into
+    # KV shares whose boundaries depend on the number of units, i.e. on the batch size: same math, different fp32 summation
+    # order, so B = 2 tracks B = 1 to rounding (amplified through 57 random blocks) instead of bit-for-bit ...
+    print(f"12B full size: B=2 row 0 vs B=1 rel-L2 {_rel(both[0], v[0]):.3e}")
+    assert _rel(both[0], v[0]) < 5e-2 and _cosdist(both[0], v[0]) < 1e-3
+    eng.set_option("attn_variant", 5)  # ... and bit-for-bit under the schedule with a fixed summation order
+    assert torch.equal(fwd(slice(0, 2), inp["img_ids"], hs)[0], fwd(one, inp["img_ids"], hs[one])[0])
+    eng.set_option("attn_variant", 0)
     # forward + scheduler.step  ==  fused step  ==  scheduled step
     sig = sch.sigmas_cpu
     x_ref = sch.step(v, t0, inp["latents"][one], return_dict=False)[0]

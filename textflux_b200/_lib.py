@@ -43,6 +43,7 @@ SIGNATURES = {
     "tfx_op_rope_table": (C.c_int, [_P, _P, _I32, _I32, C.POINTER(_I32), _P, _P]),
     "tfx_op_timestep_embed": (C.c_int, [_P, _I32, _I32, _P, _P]),
     "tfx_debug_set_attention_trace": (C.c_int, [_P]),
+    "tfx_debug_set_attention_cta_trace": (C.c_int, [_P]),
     "tfx_op_pack_latents": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, C.c_float, C.c_float, _P]),
     "tfx_op_unpack_latents": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _I32, _I32, C.c_float, C.c_float, _P]),
     "tfx_op_pack_mask": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P]),

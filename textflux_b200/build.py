@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libtextflux_b200.so")
 SOURCES = ["tfx_api.cu"]
-HEADERS = ["ptx.cuh", "gemm.cuh", "attention.cuh", "attention3.cuh", "attention_pair.cuh", "conditioning.cuh",
+HEADERS = ["ptx.cuh", "gemm.cuh", "attention_common.cuh", "attention3.cuh", "attention4.cuh", "attention5.cuh", "conditioning.cuh",
            "pointwise.cuh", "probe.cuh"]
 
 

@@ -1,5 +1,5 @@
-// Joint [text;image] flash attention, schedule 3: the ping-pong schedule of attention.cuh (two 128-row query tiles per
-// CTA, S/P/O in TMEM) rebuilt around what the clock traces of that kernel showed (profiles/r1j_attn_trace.md):
+// Joint [text;image] flash attention, schedule 3: a ping-pong schedule (two 128-row query tiles per CTA, S/P/O in TMEM)
+// built around what the clock traces of its predecessor showed (profiles/r1j_attn_trace.md):
 //   * the issuing thread was the slow link: `warp == 1 && lane == 0` is a divergent branch, so every tcgen05.mma was
 //     wrapped in a value-broadcast loop (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~15 dependent SASS instructions, about as
 //     long as the 64 cycles the MMA itself runs).  Here the whole warp walks the loop in a warp-uniform context, the
@@ -10,12 +10,12 @@
 //   * 12 warps with setmaxnreg: the producer/issuer warpgroup drops to 72 registers, the two softmax warpgroups take
 //     216 each, which holds the whole score row + packed P without spills.
 //   * no wait on pv_done inside the loop: s_full(j) already implies PV(j-1) retired (commit tracks all earlier MMAs).
-// Same arithmetic as attention.cuh: fp32 scores, lazily rescaled running max (threshold 2^8), a fraction of the
+// Arithmetic: fp32 scores, lazily rescaled running max (threshold 2^8), a fraction of the
 // exponentials on the FMA pipe (packed Cody-Waite + cubic), P rounded to bf16 for the PV MMA, fp32 O.
 #pragma once
 #include <cuda.h>
 
-#include "attention.cuh"
+#include "attention_common.cuh"
 #include "ptx.cuh"
 
 namespace tfx {
@@ -27,11 +27,11 @@ struct Attn3Cfg {
   static constexpr int kKStages = 2;
   static constexpr int kVStages = 2;
   static constexpr int kThreads = 384;                   // wg0: TMA, MMA, TMEM alloc, spare; wg1/wg2: softmax of q-tile 0/1
-  static constexpr int kXchBytes = 2 * 2 * 128 * 4;      // row-split softmax: [2 slots][2 column halves][128 rows] fp32
+  static constexpr int kXchBytes = 2 * 2 * 128 * 4;      // scratch behind the barriers (attention4: merge flag)
   static constexpr int kSmemBytes = (2 + kKStages + kVStages) * kTileBytes + 1024 + 256 + kXchBytes;
   static constexpr int kSCol = 0;    // S_q at q*128 (P_q aliases its first 64 columns)
   static constexpr int kOCol = 256;  // O_q at 256 + q*128
-  static constexpr int kRegsSmall = 72, kRegsLarge = 216;
+  static constexpr int kRegsSmall = 72, kRegsLarge = 216;  // 80 / 216 would use the register file exactly and never gets its setmaxnreg.inc granted (measured: hangs)
 };
 
 template <int kRegs>
@@ -44,14 +44,10 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 //   4 second half handed over          5 issuer saw half 0         6 PV issued       7 next QK issued
 constexpr int kAttnTraceSlots = 8;
 
-// kRowSplit: two threads per query row.  Both softmax warpgroups work on the SAME query tile (warpgroup 1 on keys 0..63 of
-// the score row, warpgroup 2 on keys 64..127; the row maximum is combined through shared memory) and alternate between the
-// two tiles, instead of one warpgroup per tile.  The traces of the one-thread-per-row form show a lone warp per SMSP
-// spending ~1400 cycles in the exponentials of a tile (in-order issue across the MUFU / FMA / ALU pipes, 0.3 IPC) while
-// the tensor pipe waits; two warps per SMSP on the same tile halve that latency at the same instruction count.
+// named barrier of the 256 softmax threads (warps 4..11)
 __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int kHeadDim, int kEmu, bool kSplitP, bool kTrace, bool kRowSplit = false>
+template <int kHeadDim, int kEmu, bool kSplitP, bool kTrace>
 __global__ void __launch_bounds__(Attn3Cfg<kHeadDim>::kThreads, 1)
 attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p) {
@@ -74,8 +70,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* p_full = s_full + 2;         // [2 q][2 halves]
   uint64_t* pv_done = p_full + 4;        // [2]
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
-  float* xch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][2][128]
-  constexpr bool kTwoBars = kSplitP || kRowSplit;
+  constexpr bool kTwoBars = kSplitP;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
@@ -85,6 +80,16 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   const int bh = b * p.H + head;
   const int n_kv = (p.N + 127) / 128;
   const bool tracing = kTrace && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  long long* ctr = nullptr;
+  if (kTrace && p.cta_trace != nullptr) {
+    ctr = p.cta_trace + ((long long)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8;
+    if (threadIdx.x == 0) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      ctr[0] = (long long)globaltimer_ns();
+      ctr[7] = smid;
+    }
+  }
   pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
@@ -112,6 +117,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   const uint32_t tmem_base = *tmem_base_ptr;
 
   pdl_wait();
+  if (kTrace && ctr && threadIdx.x == 0) ctr[1] = (long long)globaltimer_ns();
 
   if (warp < 4) {
     setmaxnreg_dec<Cfg::kRegsSmall>();
@@ -178,6 +184,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
+      if (kTrace && ctr && leader) ctr[2] = (long long)globaltimer_ns();
       issue_qk(0, 0);
       issue_qk(1, 0);
       if (leader) umma_commit(&k_empty[0]);
@@ -219,138 +226,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     }
   } else {
     setmaxnreg_inc<Cfg::kRegsLarge>();
-    if constexpr (kRowSplit) {
-      // ===================== softmax, two threads per query row, both warpgroups on the same tile =====================
-      const int half = (warp - 4) >> 2;  // keys half*64 .. half*64+63 of every score row; O / output columns likewise
-      const int quad = warp & 3;
-      const int row_in_tile = quad * 32 + lane;
-      const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16);
-      const float c = p.scale_log2;
-      const bool tr = tracing && warp == 4 && lane == 0;
-      const float kRescaleThreshold = 8.0f;
-      constexpr int kOCols = kHeadDim / 2;  // O columns owned by this thread
-      float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-      int it = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        const int valid = p.N - j * 128 - half * 64;  // >= 64 on every tile but possibly the last
-#pragma unroll
-        for (int q = 0; q < 2; ++q, ++it) {
-          const uint32_t t_s = t_lane + uint32_t(Cfg::kSCol + q * 128);
-          const uint32_t t_o = t_lane + uint32_t(Cfg::kOCol + q * 128 + half * kOCols);
-          mbar_wait(&s_full[q], j & 1);
-          tc_fence_after();
-          if (tr) p.trace[(j * 2 + q) * kAttnTraceSlots + 0] = clock64();
-          uint32_t sr[2][32];
-          tmem_ld32(t_s + half * 64, sr[0]);
-          tmem_ld32(t_s + half * 64 + 32, sr[1]);
-          tmem_ld_wait();
-          if (tr) p.trace[(j * 2 + q) * kAttnTraceSlots + 1] = clock64();
-          if (valid < 64) {
-#pragma unroll
-            for (int cch = 0; cch < 2; ++cch)
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (cch * 32 + i >= valid) sr[cch][i] = 0xff800000u;
-          }
-          float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
-            mx1 = fmaxf(mx1, __uint_as_float(sr[0][16 + i]));
-            mx2 = fmaxf(mx2, __uint_as_float(sr[1][i]));
-            mx3 = fmaxf(mx3, __uint_as_float(sr[1][16 + i]));
-          }
-          float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-          // combine with the other half of the row (same lane of the warp 4 warps up/down); slots alternate so that a
-          // thread one barrier phase ahead never overwrites a value its partner has yet to read
-          float* slot = xch + (it & 1) * 256;
-          slot[half * 128 + row_in_tile] = mx;
-          softmax_bar_sync();  // also orders every thread's S loads before any P store below (P aliases S columns)
-          mx = fmaxf(mx, slot[(half ^ 1) * 128 + row_in_tile]);
-          const bool need = (mx - m[q]) * c > kRescaleThreshold;  // true on the first tile (m = -inf)
-          const float m_new = need ? mx : m[q];
-          const float alpha = need ? ex2((m[q] - m_new) * c) : 1.0f;
-          const float mc = m_new * c;
-          if (j > 0 && __any_sync(0xffffffffu, need)) {
-#pragma unroll 1
-            for (int cch = 0; cch < kOCols / 32; ++cch) {
-              uint32_t v[32];
-              tmem_ld32(t_o + cch * 32, v);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-              tmem_st32(t_o + cch * 32, v);
-            }
-            tmem_st_wait();
-          }
-          if (tr) p.trace[(j * 2 + q) * kAttnTraceSlots + 2] = clock64();
-          const f32x2 c2 = pack2(c, c), nmc2 = pack2(-mc, -mc);
-          f32x2 sum2 = pack2(0.f, 0.f);
-          uint32_t pk[32];
-#pragma unroll
-          for (int cch = 0; cch < 2; ++cch) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const f32x2 x2 = fma2(pack2(__uint_as_float(sr[cch][i]), __uint_as_float(sr[cch][i + 1])), c2, nmc2);
-              float p0, p1;
-              if (kEmu > 0 && emu_pair<kEmu>(i >> 1)) {
-                ex2_emu2(x2, p0, p1);
-              } else {
-                float x0, x1;
-                unpack2(x2, x0, x1);
-                p0 = ex2(x0);
-                p1 = ex2(x1);
-              }
-              sum2 = add2(sum2, pack2(p0, p1));
-              pk[cch * 16 + (i >> 1)] = pack_bf16(p0, p1);
-            }
-          }
-          tmem_st32(t_s + half * 32, pk);  // P (bf16 pairs) for keys half*64.. over S columns every thread has read
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[2 * q + half]);
-          if (tr) p.trace[(j * 2 + q) * kAttnTraceSlots + 3] = clock64();
-          float sum0, sum1;
-          unpack2(sum2, sum0, sum1);
-          l[q] = l[q] * alpha + (sum0 + sum1);
-          m[q] = m_new;
-        }
-      }
-      // ---- finalize: total row sum = both halves; O / l -> bf16, token-major store of this thread's dh columns
-#pragma unroll
-      for (int q = 0; q < 2; ++q, ++it) {
-        float* slot = xch + (it & 1) * 256;
-        slot[half * 128 + row_in_tile] = l[q];
-        softmax_bar_sync();
-        const float inv_l = 1.0f / (l[q] + slot[(half ^ 1) * 128 + row_in_tile]);
-        mbar_wait(&pv_done[q], (n_kv - 1) & 1);
-        tc_fence_after();
-        const int pos = q0 + q * 128 + row_in_tile;
-        const bool row_ok = pos < p.N;
-        const long long row = (pos < p.T) ? (long long)b * p.T + pos : (long long)p.B * p.T + (long long)b * p.S + (pos - p.T);
-        __nv_bfloat16* dst = p.out + row * p.ld_out + head * kHeadDim + half * kOCols;
-        const uint32_t t_o = t_lane + uint32_t(Cfg::kOCol + q * 128 + half * kOCols);
-#pragma unroll 1
-        for (int cch = 0; cch < kOCols / 32; ++cch) {
-          uint32_t v[32];
-          tmem_ld32(t_o + cch * 32, v);
-          tmem_ld_wait();
-          if (row_ok) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst + cch * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 u;
-              u.x = pack_bf16(__uint_as_float(v[8 * i + 0]) * inv_l, __uint_as_float(v[8 * i + 1]) * inv_l);
-              u.y = pack_bf16(__uint_as_float(v[8 * i + 2]) * inv_l, __uint_as_float(v[8 * i + 3]) * inv_l);
-              u.z = pack_bf16(__uint_as_float(v[8 * i + 4]) * inv_l, __uint_as_float(v[8 * i + 5]) * inv_l);
-              u.w = pack_bf16(__uint_as_float(v[8 * i + 6]) * inv_l, __uint_as_float(v[8 * i + 7]) * inv_l);
-              d4[i] = u;
-            }
-          }
-        }
-      }
-    } else {
+    {
       // ===================== softmax warpgroups: one thread per query row =====================
       const int q = (warp - 4) >> 2;
       const int quad = warp & 3;
@@ -368,6 +244,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         mbar_wait(&s_full[q], j & 1);
         tc_fence_after();
         if (tr) p.trace[(j * 2 + q) * kAttnTraceSlots + 0] = clock64();
+        if (kTrace && ctr && j == 0 && warp == 4 && lane == 0) ctr[3] = (long long)globaltimer_ns();
         uint32_t sr[4][32];
         tmem_ld32(t_s + 0, sr[0]);
         tmem_ld32(t_s + 32, sr[1]);
@@ -452,8 +329,10 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         m = m_new;
       }
       // ---- finalize: O / l -> bf16, token-major store
+      if (kTrace && ctr && warp == 4 && lane == 0) ctr[4] = (long long)globaltimer_ns();
       mbar_wait(&pv_done[q], (n_kv - 1) & 1);
       tc_fence_after();
+      if (kTrace && ctr && warp == 4 && lane == 0) ctr[5] = (long long)globaltimer_ns();
       const float inv_l = 1.0f / l;
       const bool row_ok = pos < p.N;
       const long long row = (pos < p.T) ? (long long)b * p.T + pos : (long long)p.B * p.T + (long long)b * p.S + (pos - p.T);
@@ -464,18 +343,13 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         tmem_ld32(t_o + cch * 32, v);
         tmem_ld_wait();
         if (row_ok) {
-          uint4* d4 = reinterpret_cast<uint4*>(dst + cch * 32);
+          float xo[32];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u;
-            u.x = pack_bf16(__uint_as_float(v[8 * i + 0]) * inv_l, __uint_as_float(v[8 * i + 1]) * inv_l);
-            u.y = pack_bf16(__uint_as_float(v[8 * i + 2]) * inv_l, __uint_as_float(v[8 * i + 3]) * inv_l);
-            u.z = pack_bf16(__uint_as_float(v[8 * i + 4]) * inv_l, __uint_as_float(v[8 * i + 5]) * inv_l);
-            u.w = pack_bf16(__uint_as_float(v[8 * i + 6]) * inv_l, __uint_as_float(v[8 * i + 7]) * inv_l);
-            d4[i] = u;
-          }
+          for (int i = 0; i < 32; ++i) xo[i] = __uint_as_float(v[i]) * inv_l;
+          store_row_chunk_bf16x32(dst + cch * 32, xo);
         }
       }
+      if (kTrace && ctr && warp == 4 && lane == 0) ctr[6] = (long long)globaltimer_ns();
     }
   }
 

@@ -78,18 +78,7 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&x)[32]) {
-  uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 u;
-    u.x = pack_bf16(x[8 * i + 0], x[8 * i + 1]);
-    u.y = pack_bf16(x[8 * i + 2], x[8 * i + 3]);
-    u.z = pack_bf16(x[8 * i + 4], x[8 * i + 5]);
-    u.w = pack_bf16(x[8 * i + 6], x[8 * i + 7]);
-    d4[i] = u;
-  }
-}
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&x)[32]) { store_row_chunk_bf16x32(dst, x); }
 // kReadOnly: data never written during the kernel (bias, gates, norm weights) -> ld.global.nc
 template <bool kReadOnly = true>
 __device__ __forceinline__ void load_bf16x32(const __nv_bfloat16* src, float (&x)[32]) {

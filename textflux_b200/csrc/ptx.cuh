@@ -286,6 +286,31 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       : "memory");
 }
 
+// 32-byte global store (STG.256, sm_100): one full sector per lane per instruction -- a thread-per-row epilogue issues half
+// the LSU transactions it would with 16-byte stores.  `p` must be 32-byte aligned.
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                             uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7) : "memory");
+}
+// 32 fp32 values -> 32 bf16 (64 bytes) at dst (16-byte aligned; 32-byte aligned destinations take the wide path)
+__device__ __forceinline__ void store_row_chunk_bf16x32(__nv_bfloat16* dst, const float (&x)[32]) {
+  uint32_t u[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+    u[i] = *reinterpret_cast<uint32_t*>(&v);
+  }
+  if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+    st_global_v8(dst, u[0], u[1], u[2], u[3], u[4], u[5], u[6], u[7]);
+    st_global_v8(dst + 16, u[8], u[9], u[10], u[11], u[12], u[13], u[14], u[15]);
+  } else {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d4[i] = make_uint4(u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+  }
+}
+
 // ------------------------------------------------------------------ misc math
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -13,9 +13,11 @@
 #include <vector>
 
 #include "../../include/textflux_b200.h"
-#include "attention.cuh"
+#include <algorithm>
+
 #include "attention3.cuh"
-#include "attention_pair.cuh"
+#include "attention4.cuh"
+#include "attention5.cuh"
 #include "conditioning.cuh"
 #include "gemm.cuh"
 #include "pointwise.cuh"
@@ -206,34 +208,22 @@ void configure_kernels(std::string* err_) {
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<224, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<256, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<256, 4>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<224, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<224, 4>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 1>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<128, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128, 2>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<128, 2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<128, 2, 64>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<64, 2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<64, 2, 64>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<128, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<128, 1, 128>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention2_tcgen05_kernel<64, 1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<64, 1, 128>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 1>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 2>::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_tcgen05_kernel<64, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64, 2>::kSmemBytes));
 #define TFX_ATTN3_ATTR(DH, EMU, SPLIT, TRACE) \
   CUDA_TRY(cudaFuncSetAttribute(attention3_tcgen05_kernel<DH, EMU, SPLIT, TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg<DH>::kSmemBytes))
-  TFX_ATTN3_ATTR(128, 0, false, false); TFX_ATTN3_ATTR(128, 2, false, false); TFX_ATTN3_ATTR(128, 3, false, false); TFX_ATTN3_ATTR(128, 4, false, false);
+  TFX_ATTN3_ATTR(128, 0, false, false); TFX_ATTN3_ATTR(128, 2, false, false);
   TFX_ATTN3_ATTR(128, 0, true, false); TFX_ATTN3_ATTR(128, 2, true, false); TFX_ATTN3_ATTR(128, 3, true, false); TFX_ATTN3_ATTR(128, 4, true, false);
-  TFX_ATTN3_ATTR(128, 2, true, true); TFX_ATTN3_ATTR(128, 2, false, true);
+  TFX_ATTN3_ATTR(128, 2, true, true);
   TFX_ATTN3_ATTR(64, 0, true, false); TFX_ATTN3_ATTR(64, 2, true, false);
 #undef TFX_ATTN3_ATTR
-  CUDA_TRY(cudaFuncSetAttribute(attention_pair_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPairCfg::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_pair_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPairCfg::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_pair_tcgen05_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPairCfg::kSmemBytes));
-  CUDA_TRY(cudaFuncSetAttribute(attention_pair_tcgen05_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnPairCfg::kSmemBytes));
-#define TFX_ATTN4_ATTR(DH, EMU, TRACE) \
-  CUDA_TRY(cudaFuncSetAttribute(attention3_tcgen05_kernel<DH, EMU, true, TRACE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg<DH>::kSmemBytes))
-  TFX_ATTN4_ATTR(128, 0, false); TFX_ATTN4_ATTR(128, 2, false); TFX_ATTN4_ATTR(128, 3, false); TFX_ATTN4_ATTR(128, 4, false);
-  TFX_ATTN4_ATTR(128, 2, true); TFX_ATTN4_ATTR(64, 0, false); TFX_ATTN4_ATTR(64, 2, false);
+#define TFX_ATTN4_ATTR(DH, EMU) \
+  CUDA_TRY(cudaFuncSetAttribute(attention4_tcgen05_kernel<DH, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg<DH>::kSmemBytes))
+  TFX_ATTN4_ATTR(128, 0); TFX_ATTN4_ATTR(128, 2); TFX_ATTN4_ATTR(128, 3); TFX_ATTN4_ATTR(128, 4); TFX_ATTN4_ATTR(64, 0); TFX_ATTN4_ATTR(64, 2);
 #undef TFX_ATTN4_ATTR
+#define TFX_ATTN5_ATTR(DH, EMU) \
+  CUDA_TRY(cudaFuncSetAttribute(attention5_tcgen05_kernel<DH, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg<DH>::kSmemBytes))
+  CUDA_TRY(cudaFuncSetAttribute(attention5_tcgen05_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg<128>::kSmemBytes));
+  TFX_ATTN5_ATTR(128, 0); TFX_ATTN5_ATTR(128, 2); TFX_ATTN5_ATTR(128, 3); TFX_ATTN5_ATTR(128, 4); TFX_ATTN5_ATTR(64, 0); TFX_ATTN5_ATTR(64, 2);
+#undef TFX_ATTN5_ATTR
   CUDA_TRY(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   done = true;
 }
@@ -350,90 +340,18 @@ void launch_gemm_mc(const LaunchCtx& c, int pn, int block_n, const CUtensorMap& 
   ++*c.counter;
 }
 
-// q_tiles: 1 | 2 query tiles per CTA; emu: exponentials per 8 evaluated on the FMA pipe (0, 2, 3, 4; q_tiles == 2 only)
-void launch_attention(const LaunchCtx& c, int head_dim, int q_tiles, int emu, const CUtensorMap& tq, const CUtensorMap& tk,
-                      const CUtensorMap& tv, const AttnParams& p) {
-  std::string* err_ = c.err_;
-  REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
-  REQUIRE(q_tiles == 1 || q_tiles == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
-  ProfScope ps(c, KF_ATTN);
-  dim3 grid((p.N + 128 * q_tiles - 1) / (128 * q_tiles), p.H, p.B);
-#define TFX_ATTN(DH, QT, EMU) \
-  CUDA_TRY(launch_ex(attention_tcgen05_kernel<DH, QT, EMU>, grid, dim3(AttnCfg<DH, QT>::kThreads), AttnCfg<DH, QT>::kSmemBytes, c, 1, tq, tk, tv, p))
-  if (head_dim == 128 && q_tiles == 2) {
-    switch (emu) {
-      case 1:
-      case 2: TFX_ATTN(128, 2, 2); break;
-      case 3: TFX_ATTN(128, 2, 3); break;
-      case 4: TFX_ATTN(128, 2, 4); break;
-      default: TFX_ATTN(128, 2, 0); break;
-    }
-  } else if (head_dim == 128) {
-    TFX_ATTN(128, 1, 0);
-  } else if (q_tiles == 2) {
-    if (emu) TFX_ATTN(64, 2, 3); else TFX_ATTN(64, 2, 0);
-  } else {
-    TFX_ATTN(64, 1, 0);
-  }
-#undef TFX_ATTN
-  CUDA_TRY(cudaGetLastError());
-  ++*c.counter;
-}
-
-// "QK-ahead" schedule.  mode 2: 2 query tiles per CTA, 64-key tiles (tk/tv: 64-row boxes); mode 3: 1 query tile per
-// CTA, 128-key tiles (tk/tv: 128-row boxes).
-void launch_attention2(const LaunchCtx& c, int head_dim, int mode, const CUtensorMap& tq, const CUtensorMap& tk,
-                       const CUtensorMap& tv, const AttnParams& p) {
-  std::string* err_ = c.err_;
-  REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
-  ProfScope ps(c, KF_ATTN);
-#define TFX_ATTN2(DH, QT, KV)                                                                                              \
-  CUDA_TRY(launch_ex(attention2_tcgen05_kernel<DH, QT, KV>, dim3((p.N + 128 * QT - 1) / (128 * QT), p.H, p.B),              \
-                     dim3(Attn2Cfg<DH, QT, KV>::kThreads), Attn2Cfg<DH, QT, KV>::kSmemBytes, c, 1, tq, tk, tv, p))
-  if (mode == 3) {
-    if (head_dim == 128) TFX_ATTN2(128, 1, 128); else TFX_ATTN2(64, 1, 128);
-  } else {
-    if (head_dim == 128) TFX_ATTN2(128, 2, 64); else TFX_ATTN2(64, 2, 64);
-  }
-#undef TFX_ATTN2
-  CUDA_TRY(cudaGetLastError());
-  ++*c.counter;
-}
-
-// Schedule 3 (attention3.cuh): 2 query tiles per CTA, warp-uniform issuer, split P hand-over, setmaxnreg.
+// Schedule 3 (attention3.cuh): 2 query tiles per CTA, one CTA per (batch, head, 256 query rows).
 // emu: exponentials per 8 on the FMA pipe (0, 2, 3, 4); split: hand P over in two halves; trace: clock stamps of CTA 0
-// rowsplit: two threads per query row, both softmax warpgroups on the same tile (implies the two-barrier hand-over)
 void launch_attention3(const LaunchCtx& c, int head_dim, int emu, bool split, bool trace, const CUtensorMap& tq,
-                       const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p, bool rowsplit = false) {
+                       const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p) {
   std::string* err_ = c.err_;
   REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
   ProfScope ps(c, KF_ATTN);
   dim3 grid((p.N + 255) / 256, p.H, p.B);
-  if (rowsplit) {
-#define TFX_ATTN4(DH, EMU, TRACE) \
-  CUDA_TRY(launch_ex(attention3_tcgen05_kernel<DH, EMU, true, TRACE, true>, grid, dim3(Attn3Cfg<DH>::kThreads), Attn3Cfg<DH>::kSmemBytes, c, 1, tq, tk, tv, p))
-    if (head_dim == 128 && trace) {
-      TFX_ATTN4(128, 2, true);
-    } else if (head_dim == 128) {
-      switch (emu) {
-        case 1:
-        case 2: TFX_ATTN4(128, 2, false); break;
-        case 3: TFX_ATTN4(128, 3, false); break;
-        case 4: TFX_ATTN4(128, 4, false); break;
-        default: TFX_ATTN4(128, 0, false); break;
-      }
-    } else {
-      if (emu) TFX_ATTN4(64, 2, false); else TFX_ATTN4(64, 0, false);
-    }
-#undef TFX_ATTN4
-    CUDA_TRY(cudaGetLastError());
-    ++*c.counter;
-    return;
-  }
 #define TFX_ATTN3(DH, EMU, SPLIT, TRACE) \
   CUDA_TRY(launch_ex(attention3_tcgen05_kernel<DH, EMU, SPLIT, TRACE>, grid, dim3(Attn3Cfg<DH>::kThreads), Attn3Cfg<DH>::kSmemBytes, c, 1, tq, tk, tv, p))
   if (head_dim == 128 && trace) {
-    if (split) TFX_ATTN3(128, 2, true, true); else TFX_ATTN3(128, 2, false, true);
+    TFX_ATTN3(128, 2, true, true);
   } else if (head_dim == 128 && split) {
     switch (emu) {
       case 1:
@@ -443,13 +361,7 @@ void launch_attention3(const LaunchCtx& c, int head_dim, int emu, bool split, bo
       default: TFX_ATTN3(128, 0, true, false); break;
     }
   } else if (head_dim == 128) {
-    switch (emu) {
-      case 1:
-      case 2: TFX_ATTN3(128, 2, false, false); break;
-      case 3: TFX_ATTN3(128, 3, false, false); break;
-      case 4: TFX_ATTN3(128, 4, false, false); break;
-      default: TFX_ATTN3(128, 0, false, false); break;
-    }
+    if (emu) TFX_ATTN3(128, 2, false, false); else TFX_ATTN3(128, 0, false, false);
   } else {
     if (emu) TFX_ATTN3(64, 2, true, false); else TFX_ATTN3(64, 0, true, false);
   }
@@ -458,26 +370,146 @@ void launch_attention3(const LaunchCtx& c, int head_dim, int emu, bool split, bo
   ++*c.counter;
 }
 
-// CTA-pair schedule (attention_pair.cuh), head_dim 128 only: one query tile per CTA, clusters of 2, cta_group::2 MMAs.
-// tq / tv: 128-row boxes, tk64: 64-row boxes (each CTA loads half of a K tile).
-void launch_attention_pair(const LaunchCtx& c, int emu, const CUtensorMap& tq, const CUtensorMap& tk64, const CUtensorMap& tv,
-                           const AttnParams& p) {
-  std::string* err_ = c.err_;
-  ProfScope ps(c, KF_ATTN);
-  const int nq = (p.N + 127) / 128;
-  dim3 grid(2 * ((nq + 1) / 2), p.H, p.B);
-#define TFX_ATTNP(EMU) \
-  CUDA_TRY(launch_ex(attention_pair_tcgen05_kernel<EMU>, grid, dim3(AttnPairCfg::kThreads), AttnPairCfg::kSmemBytes, c, 2, tq, tk64, tv, p))
-  switch (emu) {
-    case 1:
-    case 2: TFX_ATTNP(2); break;
-    case 3: TFX_ATTNP(3); break;
-    case 4: TFX_ATTNP(4); break;
-    default: TFX_ATTNP(0); break;
+// Schedule 4 (attention4.cuh): schedule 3 with the units of the last, partial wave cut into equal KV shares.
+struct Attn4Workspace {
+  float* ws_o = nullptr;
+  float* ws_ml = nullptr;
+  int* counters = nullptr;
+  static size_t o_bytes(int head_dim) { return (size_t)kAttn4MaxShares * 2 * 2 * head_dim * 128 * sizeof(float); }
+  static size_t ml_bytes() { return (size_t)kAttn4MaxShares * 2 * 2 * 2 * 128 * sizeof(float); }
+  static size_t counter_bytes() { return (size_t)kAttn4MaxShares * sizeof(int); }
+};
+
+// Fills the decomposition fields of `pp` for B*H*ceil(N/256) units on `sms` SMs (see attention4.cuh).
+void plan_attention4(Attn4Params& pp, int sms) {
+  const AttnParams& a = pp.a;
+  const int n_kv = (a.N + 127) / 128;
+  if (sms > kAttn4MaxShares) sms = kAttn4MaxShares;
+  pp.n_qpairs = (a.N + 255) / 256;
+  pp.n_units = a.B * a.H * pp.n_qpairs;
+  pp.n_full = pp.n_units / sms * sms;
+  pp.n_rem = pp.n_units - pp.n_full;
+  pp.stream_ctas = 0; pp.share = n_kv; pp.n_seg2 = 0;
+  if (pp.n_rem == 0) return;
+  const long long total = (long long)pp.n_rem * n_kv;
+  int share = (int)((total + sms - 1) / sms);
+  // a partial wave that is nearly full gains nothing from being cut (the merges cost about two iterations)
+  if (share * 20 > n_kv * 17) { pp.n_full = pp.n_units; pp.n_rem = 0; return; }
+  share = std::max(share, std::min(4, n_kv));                               // do not cut below 4 iterations per CTA
+  share = std::max(share, (n_kv + kAttn4MaxParts - 2) / (kAttn4MaxParts - 1));  // at most kAttn4MaxParts parts per unit
+  share = std::min(share, n_kv);
+  pp.share = share;
+  pp.stream_ctas = (int)((total + share - 1) / share);
+  // shares that cross a unit boundary get a second CTA; longest second segment first (see attention4.cuh)
+  std::vector<std::pair<int, int>> seg2;  // (-length, share)
+  for (int c = 0; c < pp.stream_ctas; ++c) {
+    const long long start = (long long)c * share, end = std::min(start + share, total);
+    const long long u0 = start / n_kv, u1 = (end - 1) / n_kv;
+    if (u1 != u0) seg2.push_back({-(int)(end - u1 * n_kv), c});
   }
-#undef TFX_ATTNP
+  std::sort(seg2.begin(), seg2.end());
+  pp.n_seg2 = (int)seg2.size();
+  for (int i = 0; i < pp.n_seg2; ++i) pp.seg2_share[i] = (uint16_t)seg2[i].second;
+}
+
+void launch_attention4(const LaunchCtx& c, int head_dim, int emu, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnParams& p, const Attn4Workspace& ws) {
+  std::string* err_ = c.err_;
+  REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
+  REQUIRE(ws.ws_o && ws.ws_ml && ws.counters, TFX_ERR_STATE, "attention workspace missing");
+  ProfScope ps(c, KF_ATTN);
+  Attn4Params pp;
+  memset(&pp, 0, sizeof pp);
+  pp.a = p;
+  pp.ws_o = ws.ws_o; pp.ws_ml = ws.ws_ml; pp.counters = ws.counters;
+  plan_attention4(pp, num_sms(c.device));
+  dim3 grid(pp.n_full + pp.stream_ctas + pp.n_seg2);
+#define TFX_ATTN4(DH, EMU) \
+  CUDA_TRY(launch_ex(attention4_tcgen05_kernel<DH, EMU>, grid, dim3(Attn3Cfg<DH>::kThreads), Attn3Cfg<DH>::kSmemBytes, c, 1, tq, tk, tv, pp))
+  if (head_dim == 128) {
+    switch (emu) {
+      case 1:
+      case 2: TFX_ATTN4(128, 2); break;
+      case 3: TFX_ATTN4(128, 3); break;
+      case 4: TFX_ATTN4(128, 4); break;
+      default: TFX_ATTN4(128, 0); break;
+    }
+  } else {
+    if (emu) TFX_ATTN4(64, 2); else TFX_ATTN4(64, 0);
+  }
+#undef TFX_ATTN4
   CUDA_TRY(cudaGetLastError());
   ++*c.counter;
+}
+
+// Schedule 5 (attention5.cuh): one persistent CTA per SM walking whole units, then its share of the remainder stream.
+void plan_attention5(Attn5Params& pp, int sms) {
+  const AttnParams& a = pp.a;
+  const int n_kv = (a.N + 127) / 128;
+  const int G = std::min(sms, kAttn4MaxShares);
+  pp.n_qpairs = (a.N + 255) / 256;
+  pp.n_units = a.B * a.H * pp.n_qpairs;
+  pp.n_waves = pp.n_units / G;
+  pp.n_rem = pp.n_units - pp.n_waves * G;
+  pp.share = 0; pp.stream_ctas = 0;
+  if (pp.n_rem > 0) {
+    const long long total = (long long)pp.n_rem * n_kv;
+    int share = (int)((total + G - 1) / G);
+    if (share * 20 > n_kv * 17) share = n_kv;                                   // nearly full partial wave: whole units, no merges
+    share = std::max(share, std::min(4, n_kv));                                   // do not cut below 4 iterations
+    share = std::max(share, (n_kv + kAttn4MaxParts - 2) / (kAttn4MaxParts - 1));  // at most kAttn4MaxParts parts per unit
+    share = std::min(share, n_kv);
+    pp.share = share;
+    pp.stream_ctas = (int)((total + share - 1) / share);
+  }
+  pp.grid = pp.n_waves > 0 ? G : std::max(pp.stream_ctas, 1);
+}
+
+void launch_attention5(const LaunchCtx& c, int head_dim, int emu, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnParams& p, const Attn4Workspace& ws, bool trace = false) {
+  std::string* err_ = c.err_;
+  REQUIRE(head_dim == 64 || head_dim == 128, TFX_ERR_INVALID, "attention_head_dim %d unsupported (64 or 128)", head_dim);
+  REQUIRE(ws.ws_o && ws.ws_ml && ws.counters, TFX_ERR_STATE, "attention workspace missing");
+  ProfScope ps(c, KF_ATTN);
+  Attn5Params pp;
+  memset(&pp, 0, sizeof pp);
+  pp.a = p;
+  pp.ws_o = ws.ws_o; pp.ws_ml = ws.ws_ml; pp.counters = ws.counters;
+  plan_attention5(pp, num_sms(c.device));
+  dim3 grid(pp.grid);
+#define TFX_ATTN5(DH, EMU) \
+  CUDA_TRY(launch_ex(attention5_tcgen05_kernel<DH, EMU>, grid, dim3(Attn3Cfg<DH>::kThreads), Attn3Cfg<DH>::kSmemBytes, c, 1, tq, tk, tv, pp))
+  if (head_dim == 128 && trace) {
+    CUDA_TRY(launch_ex(attention5_tcgen05_kernel<128, 2, true>, grid, dim3(Attn3Cfg<128>::kThreads), Attn3Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, pp));
+  } else if (head_dim == 128) {
+    switch (emu) {
+      case 1:
+      case 2: TFX_ATTN5(128, 2); break;
+      case 3: TFX_ATTN5(128, 3); break;
+      case 4: TFX_ATTN5(128, 4); break;
+      default: TFX_ATTN5(128, 0); break;
+    }
+  } else {
+    if (emu) TFX_ATTN5(64, 2); else TFX_ATTN5(64, 0);
+  }
+#undef TFX_ATTN5
+  CUDA_TRY(cudaGetLastError());
+  ++*c.counter;
+}
+
+// attn_variant 0 ("auto"): schedule 5 where its work decomposition pays, schedule 3 elsewhere.  Measured (tools/bench_kernels.py,
+// profiles/r2e_kernels_attn.json, 24 heads, TFLOP/s, schedule 3 / schedule 5): N = 2560 936 / 865, 4608 1287 / 1249, 5120 1131 /
+// 1229, 8704 1321 / 1319, 12800 1313 / 1274 -- schedule 5 wins when every SM runs at least two whole units before the shared
+// remainder and the remainder is cut into few parts (each part costs a 5 us park, each cut unit a 6-11 us merge).
+int pick_attention_variant(const AttnParams& a, int sms) {
+  Attn5Params pp;
+  memset(&pp, 0, sizeof pp);
+  pp.a = a;
+  plan_attention5(pp, sms);
+  const int n_kv = (a.N + 127) / 128;
+  if (pp.n_waves < 2 || pp.n_rem == 0 || pp.share >= n_kv) return 5;
+  const int parts = (n_kv + pp.share - 1) / pp.share + 1;
+  return parts <= 5 ? 9 : 5;
 }
 
 void launch_ln_modulate(const LaunchCtx& c, const LnModParams& p) {
@@ -533,9 +565,9 @@ struct tfx_model {
   long long graph_nodes = 0;
   int gemm_cta_group = 2;  // 2-CTA 256x256 tiles: the configuration every published number was measured with
   int gemm_mcast = 0;  // 0: plain kernels; 2|4: pairs per cluster sharing A by TMA multicast
-  int attn_q_tiles = 2;
-  int attn_variant = 5;  // 1: v1 schedule (attn_q_tiles, attn_emu apply); 2, 3: QK-ahead schedules (measured slower);
-                         // 4, 5, 6: schedule 3 (attention3.cuh) whole-P / split-P (default, fastest) / row-split softmax
+  int attn_variant = 0;  // 0: per shape, 5 or 9 (pick_attention_variant); 4, 5: schedule 3 (attention3.cuh) whole-P / split-P hand-over, one CTA per (head, 256 query rows);
+                         // 8: schedule 4 (attention4.cuh): schedule 3 split-P + the last partial wave cut into KV shares;
+                         // 9: schedule 5 (attention5.cuh): persistent CTAs, items overlapped, remainder cut into KV shares
   int gemm_narrow_tiles = 1;  // allow 224-wide tiles where they cut wave quantisation (option "gemm_narrow_tiles")
   int gemm_l2_hints = 0;  // bit 0: A (activation) loads evict_last, bit 1: B (weight) loads evict_first (option "gemm_l2_hints")
   int attn_emu = 2;  // column pairs per 8 whose exponentials run on the FMA pipe (packed polynomial) instead of MUFU:
@@ -567,7 +599,8 @@ struct tfx_model {
   // activation-side TMA descriptors, [0] text rows, [1] image rows
   enum AKind { A_NBUF = 0, A_ATTN = 1, A_MLP = 2, A_CAT = 3, A_X = 4, A_ENC = 5, A_KINDS = 6 };
   CUtensorMap mA[2][A_KINDS][2];  // [0: 128-row boxes | 1: 128/gemm_mcast-row boxes for the multicast kernels][kind][group]
-  CUtensorMap mQ, mK, mV, mK64, mV64;  // 128-row boxes (v1 schedule) and 64-row K/V boxes (QK-ahead schedule)
+  CUtensorMap mQ, mK, mV;  // [B*H, N, dh] with 128-row boxes
+  Attn4Workspace attn_ws;  // partial (O, m, l) of the KV shares of schedule 4
   std::map<std::string, CUtensorMap> mB;  // weight-side descriptors, keyed "<weight>#<cta_group>#<block_n>"
 
   cudaStream_t stream = nullptr;
@@ -718,8 +751,10 @@ void tfx_model::prepare(int B_, int S_, int T_) {
   mQ = make_map_3d(err_, q, (long long)B * H, N, dh);
   mK = make_map_3d(err_, k, (long long)B * H, N, dh);
   mV = make_map_3d(err_, v, (long long)B * H, N, dh);
-  mK64 = make_map_3d(err_, k, (long long)B * H, N, dh, 64);
-  mV64 = make_map_3d(err_, v, (long long)B * H, N, dh, 64);
+  attn_ws.ws_o = reinterpret_cast<float*>(alloc<uint8_t>(Attn4Workspace::o_bytes(dh)));
+  attn_ws.ws_ml = reinterpret_cast<float*>(alloc<uint8_t>(Attn4Workspace::ml_bytes()));
+  attn_ws.counters = reinterpret_cast<int*>(alloc<uint8_t>(Attn4Workspace::counter_bytes()));
+  CUDA_TRY(cudaMemset(attn_ws.counters, 0, Attn4Workspace::counter_bytes()));
 }
 
 // The launch sequence of one FluxTransformer2DModel.forward (+ optional fused Euler update).
@@ -816,6 +851,8 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
   ap.scale_log2 = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
   ap.out = cat; ap.ld_out = 5LL * D;
 
+  const int av = attn_variant ? attn_variant : pick_attention_variant(ap, num_sms(device));
+
   LnModParams lp;
   lp.x = hidden; lp.y = nbuf; lp.rows = (int)(rt + ri); lp.D = D; lp.row_begin = 0; lp.rows0 = (int)rt;
   lp.rows_per0 = T; lp.rows_per1 = S; lp.mod = mod; lp.mod_stride = mod_rows; lp.eps = 1e-6f;
@@ -840,11 +877,9 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
       }
       gemm(c, 256, A_NBUF, name("d%d.qkv_c", i, ".w"), name("d%d.qkv_x", i, ".w"), p);
     }
-    if (attn_variant == 2) launch_attention2(c, dh, 2, mQ, mK64, mV64, ap);
-    else if (attn_variant == 3) launch_attention2(c, dh, 3, mQ, mK, mV, ap);
-    else if (attn_variant == 7 && dh == 128) launch_attention_pair(c, attn_emu, mQ, mK64, mV, ap);
-    else if (attn_variant >= 4) launch_attention3(c, dh, attn_emu, attn_variant != 4, false, mQ, mK, mV, ap, attn_variant == 6);
-    else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
+    if (av == 9) launch_attention5(c, dh, attn_emu, mQ, mK, mV, ap, attn_ws);
+    else if (av == 8) launch_attention4(c, dh, attn_emu, mQ, mK, mV, ap, attn_ws);
+    else launch_attention3(c, dh, attn_emu, av != 4, false, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, D);
       p.mode0 = EPI_GATE_RES;
@@ -896,11 +931,9 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
       const std::string wn = name("s%d.qkvmlp", j, ".w");
       gemm(c, 256, A_NBUF, wn, wn, p);
     }
-    if (attn_variant == 2) launch_attention2(c, dh, 2, mQ, mK64, mV64, ap);
-    else if (attn_variant == 3) launch_attention2(c, dh, 3, mQ, mK, mV, ap);
-    else if (attn_variant == 7 && dh == 128) launch_attention_pair(c, attn_emu, mQ, mK64, mV, ap);
-    else if (attn_variant >= 4) launch_attention3(c, dh, attn_emu, attn_variant != 4, false, mQ, mK, mV, ap, attn_variant == 6);
-    else launch_attention(c, dh, attn_q_tiles, attn_emu, mQ, mK, mV, ap);
+    if (av == 9) launch_attention5(c, dh, attn_emu, mQ, mK, mV, ap, attn_ws);
+    else if (av == 8) launch_attention4(c, dh, attn_emu, mQ, mK, mV, ap, attn_ws);
+    else launch_attention3(c, dh, attn_emu, av != 4, false, mQ, mK, mV, ap);
     {
       GemmParams p = base_params(D, 5 * D);
       p.mode0 = EPI_GATE_RES;
@@ -1049,11 +1082,8 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
     REQUIRE(value == 0 || value == 2 || value == 4, TFX_ERR_INVALID, "gemm_mcast must be 0, 2 or 4");
     h->gemm_mcast = (int)value;
     h->free_workspace();  // A-side descriptors depend on it: the next tfx_prepare rebuilds them
-  } else if (k == "attn_q_tiles") {
-    REQUIRE(value == 1 || value == 2, TFX_ERR_INVALID, "attn_q_tiles must be 1 or 2");
-    h->attn_q_tiles = (int)value;
   } else if (k == "attn_variant") {
-    REQUIRE(value >= 1 && value <= 7, TFX_ERR_INVALID, "attn_variant must be 1..7");
+    REQUIRE(value == 0 || value == 4 || value == 5 || value == 8 || value == 9, TFX_ERR_INVALID, "attn_variant must be 0, 4, 5, 8 or 9");
     h->attn_variant = (int)value;
   } else if (k == "attn_emu") {
     REQUIRE(value == 0 || (value >= 2 && value <= 4), TFX_ERR_INVALID, "attn_emu must be 0, 2, 3 or 4");
@@ -1459,8 +1489,13 @@ int tfx_op_linear_euler(const void* A, int64_t lda, const void* Wt, const void* 
 }
 
 static void* g_attn_trace = nullptr;
+static void* g_attn_cta_trace = nullptr;
 int tfx_debug_set_attention_trace(void* dev_ptr) {
   g_attn_trace = dev_ptr;
+  return TFX_OK;
+}
+int tfx_debug_set_attention_cta_trace(void* dev_ptr) {
+  g_attn_cta_trace = dev_ptr;
   return TFX_OK;
 }
 
@@ -1482,21 +1517,25 @@ int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int
     p.scale_log2 = (1.0f / sqrtf((float)head_dim)) * 1.4426950408889634f;
     p.out = reinterpret_cast<bf16*>(out); p.ld_out = ld_out;
     LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
-    if (q_tiles == 3) {
-      CUtensorMap mk64 = make_map_3d(err_, k, (long long)B * H, N, head_dim, 64);
-      CUtensorMap mv64 = make_map_3d(err_, v, (long long)B * H, N, head_dim, 64);
-      launch_attention2(c, head_dim, 2, mq, mk64, mv64, p);
-    } else if (q_tiles == 4) {
-      launch_attention2(c, head_dim, 3, mq, mk, mv, p);
-    } else if (q_tiles % 10 == 8) {  // CTA-pair schedule (head_dim 128), + 10*emu
-      REQUIRE(head_dim == 128, TFX_ERR_INVALID, "the CTA-pair attention schedule needs head_dim 128");
-      CUtensorMap mk64 = make_map_3d(err_, k, (long long)B * H, N, head_dim, 64);
-      launch_attention_pair(c, (q_tiles / 10) % 10, mq, mk64, mv, p);
-    } else if (q_tiles % 10 >= 5 && q_tiles % 10 <= 7) {  // schedule 3: 5 = whole-P hand-over, 6 = split, 7 = row-split softmax; + 10*emu; + 100 trace
+    const int sched = q_tiles % 10, emu = (q_tiles / 10) % 10;
+    if (sched == 9 || sched == 7) {  // schedule 4 (stream) | schedule 5 (persistent stream): + 10 * emu
+      static std::map<int, Attn4Workspace> ws_on;  // per device, sized for the largest head_dim
+      Attn4Workspace& ws = ws_on[dev];
+      if (!ws.ws_o) {
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ws.ws_o), Attn4Workspace::o_bytes(128)));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ws.ws_ml), Attn4Workspace::ml_bytes()));
+        CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&ws.counters), Attn4Workspace::counter_bytes()));
+        CUDA_TRY(cudaMemset(ws.counters, 0, Attn4Workspace::counter_bytes()));
+      }
+      p.cta_trace = reinterpret_cast<long long*>(g_attn_cta_trace);
+      if (sched == 9) launch_attention4(c, head_dim, emu, mq, mk, mv, p, ws);
+      else launch_attention5(c, head_dim, emu, mq, mk, mv, p, ws, q_tiles >= 100);
+    } else if (sched == 5 || sched == 6) {  // schedule 3: 5 = whole-P hand-over, 6 = split; + 10 * emu; + 100 trace
       p.trace = reinterpret_cast<long long*>(g_attn_trace);
-      launch_attention3(c, head_dim, (q_tiles / 10) % 10, q_tiles % 10 == 6, q_tiles >= 100, mq, mk, mv, p, q_tiles % 10 == 7);
+      p.cta_trace = reinterpret_cast<long long*>(g_attn_cta_trace);
+      launch_attention3(c, head_dim, emu, sched == 6, q_tiles >= 100, mq, mk, mv, p);
     } else {
-      launch_attention(c, head_dim, q_tiles % 10, q_tiles / 10, mq, mk, mv, p);
+      REQUIRE(false, TFX_ERR_INVALID, "attention schedule code %d unknown (5 | 6 | 7 | 9, + 10 * emu)", q_tiles);
     }
   } catch (const Fail& f) {
     return f.code;

@@ -67,8 +67,8 @@ class B200FluxTransformer(torch.nn.Module):
     """
 
     def __init__(self, config, get: Callable[[str], Tensor], device: Union[str, torch.device] = "cuda",
-                 gemm_cta_group: Optional[int] = None, attn_q_tiles: Optional[int] = None, use_graph: bool = True,
-                 gemm_mcast: Optional[int] = None, lora_modules=None):
+                 gemm_cta_group: Optional[int] = None, use_graph: bool = True, gemm_mcast: Optional[int] = None,
+                 lora_modules=None):
         """`lora_modules`: reference module names whose weights `get` returns with an adapter already folded in (a
         `fold_lora` getter); recorded so that a later `load_lora_weights` / `unload_lora_weights` restores them."""
         super().__init__()
@@ -95,8 +95,6 @@ class B200FluxTransformer(torch.nn.Module):
         _lib.check(self._lib.tfx_finalize_weights(self._h), self._h)
         if gemm_cta_group is not None:
             self.set_option("gemm_cta_group", gemm_cta_group)
-        if attn_q_tiles is not None:
-            self.set_option("attn_q_tiles", attn_q_tiles)
         self._shape: Optional[Tuple[int, int, int]] = None
         folded = getattr(get, "lora_modules", None) if lora_modules is None else lora_modules
         self._lora_modules: set = set(folded or ())

@@ -33,7 +33,7 @@ def main():
     v = torch.randn(1, H, N, dh, device="cuda").to(torch.bfloat16)
     out = torch.empty(N, H * dh, device="cuda", dtype=torch.bfloat16)
     res = {}
-    for code, name in ((125, "whole-P"), (126, "split-P"), (127, "row-split")):  # 100 + tfx_op_attention q_tiles code
+    for code, name in ((125, "whole-P"), (126, "split-P")):  # 100 + tfx_op_attention q_tiles code
         tr = torch.zeros(n_kv * 2 * 8, dtype=torch.int64, device="cuda")
         _lib.check(lib.tfx_debug_set_attention_trace(tr.data_ptr()))
         for _ in range(3):
