@@ -49,7 +49,7 @@ int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
 void tfx_destroy(tfx_handle h);
 /* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
 const char* tfx_last_error(tfx_handle h);
-/* "gemm_narrow_tiles" (0|1: allow 224-wide GEMM tiles against wave quantisation), "gemm_l2_hints" (0..3: bit 0 activations evict_last, bit 1 weights evict_first in the GEMM's TMA loads), "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (0 = per shape, schedule 3 or 5 (default); 4 | 5 = schedule 3 whole-P / split-P, 8 = schedule 4 stream, 9 = schedule 5 persistent stream), "attn_emu" (0|2|3|4), "use_graph" (0|1), "mod_cache_slots" (0..4096: device-side cache of modulation vectors keyed on the (timestep, guidance, pooled) bits tfx_forward / tfx_step receive; 0 = recompute every call), "mod_cache_reset" (drop every cached modulation vector: call after rewriting weights in place), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
+/* "gemm_narrow_tiles" (0|1: allow 224-wide GEMM tiles against wave quantisation), "gemm_m_band" (-1..64: tile order of the wide-K GEMMs, -1 = per shape (default), 0 = M-fastest, b = bands of b M tiles), "gemm_l2_hints" (0..3: bit 0 activations evict_last, bit 1 weights evict_first in the GEMM's TMA loads), "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (0 = per shape, schedule 3 or 5 (default); 4 | 5 = schedule 3 whole-P / split-P, 8 = schedule 4 stream, 9 = schedule 5 persistent stream), "attn_emu" (0|2|3|4), "use_graph" (0|1), "mod_cache_slots" (0..4096: device-side cache of modulation vectors keyed on the (timestep, guidance, pooled) bits tfx_forward / tfx_step receive; 0 = recompute every call), "mod_cache_reset" (drop every cached modulation vector: call after rewriting weights in place), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
  * pair per kernel, summed per family; resets the sums) */
 int tfx_set_option(tfx_handle h, const char* key, int64_t value);
 /* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step;
@@ -61,6 +61,13 @@ int tfx_get_counter(tfx_handle h, const char* key, int64_t* value);
 /* Registers a bf16 device tensor [rows, cols] (row-major, 16-byte aligned) under a packed-layout name.
  * The caller keeps the memory alive for the handle's lifetime. */
 int tfx_set_weight(tfx_handle h, const char* name, const void* dev_ptr, int64_t rows, int64_t cols);
+/* Unfused LoRA, the form the reference runs at inference (run_inference_lora.py:52-65; PEFT Linear.forward:
+ * base(x) + scaling * lora_B(lora_A(x))): next to a packed matrix "<m>.w" [N, K] register "<m>.la" [64, K] (the lora_A rows of
+ * the modules packed into it, zero padded to 64) and "<m>.lb" [N, 64] (scaling * lora_B of each module in that module's rows
+ * and rank columns).  The GEMM of "<m>" then accumulates x W^T + bf16(x la^T) lb^T in one fp32 accumulator before its epilogue;
+ * the base weight is not modified.  tfx_unset_weight removes a registered tensor (both ".la" and ".lb" to drop an adapter);
+ * call tfx_finalize_weights again after either. */
+int tfx_unset_weight(tfx_handle h, const char* name);
 int tfx_finalize_weights(tfx_handle h);
 
 /* ---- per-request set-up --------------------------------------------------------------------------------------- */
@@ -113,6 +120,11 @@ int tfx_step_scheduled(tfx_handle h, int32_t step_index, const void* latents_in,
  * cta_group: 1 | 2 plain kernels, 22 | 24 multicast kernel with 2 | 4 CTA pairs per cluster */
 int tfx_op_linear(const void* A, int64_t lda, const void* W, const void* bias, void* out, int64_t ldo, int32_t M,
                   int32_t N, int32_t K, int32_t mode, const void* gate, const void* res, int32_t cta_group, void* stream);
+/* tfx_op_linear with the unfused-LoRA side path: Y = epilogue(A W^T + bf16(A la^T) lb^T + bias), la [64, K], lb [N, 64];
+ * t_scratch [M, 64] bf16 receives bf16(A la^T).  m_band: GEMM tile order (0 = M-fastest; b > 0 = bands of b M tiles). */
+int tfx_op_linear_lora(const void* A, int64_t lda, const void* W, const void* bias, const void* la, const void* lb, void* t_scratch,
+                       void* out, int64_t ldo, int32_t M, int32_t N, int32_t K, int32_t mode, const void* gate, const void* res,
+                       int32_t cta_group, int32_t m_band, void* stream);
 /* The fused QKV projection of one stream, as the engine launches it for attention_processor.py:1987-2037: Y = A W^T + bias
  * with W [3*H*dh, K] = to_q;to_k;to_v, then per head RMSNorm(q), RMSNorm(k) (normalization.py:532-549, weights rms_q/rms_k
  * [dh]) and apply_rotary_emb (embeddings.py:879-925) with the (cos,sin) table rope_f32 [n_joint, dh/2, 2], scattered

@@ -26,6 +26,7 @@ SIGNATURES = {
     "tfx_set_option": (C.c_int, [_P, C.c_char_p, _I64]),
     "tfx_get_counter": (C.c_int, [_P, C.c_char_p, C.POINTER(_I64)]),
     "tfx_set_weight": (C.c_int, [_P, C.c_char_p, _P, _I64, _I64]),
+    "tfx_unset_weight": (C.c_int, [_P, C.c_char_p]),
     "tfx_finalize_weights": (C.c_int, [_P]),
     "tfx_prepare": (C.c_int, [_P, _I32, _I32, _I32]),
     "tfx_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
@@ -35,6 +36,7 @@ SIGNATURES = {
     "tfx_set_schedule": (C.c_int, [_P, _P, _I32, _P, _P, _P]),
     "tfx_step_scheduled": (C.c_int, [_P, _I32, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P]),
     "tfx_op_linear": (C.c_int, [_P, _I64, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _P]),
+    "tfx_op_linear_lora": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _I32, _I32, _P]),
     "tfx_op_linear_qkv": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P]),
     "tfx_op_linear_euler": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
     "tfx_op_attention": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _P]),

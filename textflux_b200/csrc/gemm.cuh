@@ -59,6 +59,14 @@ struct GemmParams {
   float rms_eps;
   const float* dt_ptr;  // EULER: device scalar float(bf16(sigma_next - sigma))
   int debug_flags;      // bit 0: A loads with L2 evict_last, bit 1: B (weight) loads with L2 evict_first
+  int m_band;           // tile order: 0 = M-fastest over all M tiles (a wave spans every M tile and a few N tiles: each weight tile
+                        // is fetched once, A must stay in L2); b > 0 = bands of b M tiles, inside a band M-fastest over all N tiles
+                        // (a wave spans b M tiles x all N tiles: for wide-K GEMMs whose A is larger than the L2)
+  int k_ext;            // 0 | 64: one extra k-block behind the K of A whose operands come from the extension descriptors
+                        // (A side tmE0 / tmE1: [M, 64]; W side tmF0 / tmF1: [N, 64]).  Unfused LoRA rides here: with
+                        // T = bf16(x A_lora^T) as the A extension and (alpha/r) B_lora as the W extension the accumulator holds
+                        // x W^T + (alpha/r) T B^T before any epilogue runs -- PEFT's `base(x) + scaling * lora_B(lora_A(x))`
+                        // (run_inference_lora.py:52-65 keeps the adapters unfused) without touching the base weight
 };
 
 constexpr int kGemmBlockN = 256;  // default tile width; 224 / 192 are instantiated to cut wave quantisation
@@ -225,10 +233,22 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int grp,
   }
 }
 
+// tile index -> (M tile, N tile) under GemmParams::m_band
+__device__ __forceinline__ void gemm_tile_coords(int t, int MT, int NT, int band, int& mi, int& ni) {
+  if (band <= 0 || band >= MT) { mi = t % MT; ni = t / MT; return; }
+  const int per = band * NT;
+  const int b = t / per, r = t - b * per;
+  const int rows = min(band, MT - b * band);
+  ni = r / rows;
+  mi = b * band + (r - ni * rows);
+}
+
 template <int kCtaGroup, int kBN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                     const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                    const __grid_constant__ CUtensorMap tmE0, const __grid_constant__ CUtensorMap tmE1,
+                    const __grid_constant__ CUtensorMap tmF0, const __grid_constant__ CUtensorMap tmF1,
                     const __grid_constant__ GemmParams p) {
   using Cfg = GemmCfg<kCtaGroup, kBN>;
   constexpr int kStages = Cfg::kStages;
@@ -254,6 +274,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     if (p.num_groups > 1) {
       prefetch_tensormap(&tmA1);
       prefetch_tensormap(&tmB1);
+    }
+    if (p.k_ext) {
+      prefetch_tensormap(&tmE0);
+      prefetch_tensormap(&tmF0);
+      if (p.num_groups > 1) {
+        prefetch_tensormap(&tmE1);
+        prefetch_tensormap(&tmF1);
+      }
     }
   }
   if (warp == 1 && lane == 0) {
@@ -283,7 +311,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   const int MT = mt0 + mt1;
   const int NT = (p.N + kBN - 1) / kBN;
   const int num_tiles = MT * NT;
-  const int KB = p.K / kGemmBlockK;
+  const int KBm = p.K / kGemmBlockK;                 // k-blocks whose A operand is the main descriptor
+  const int KB = KBm + p.k_ext / kGemmBlockK;        // + the extension block (0 or 1)
   const int first_tile = blockIdx.x / kCtaGroup;
   const int tile_step = gridDim.x / kCtaGroup;
 
@@ -295,24 +324,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     const uint64_t hint_a = (p.debug_flags & 1) ? kEvictLast : kEvictNormal;
     const uint64_t hint_b = (p.debug_flags & 2) ? kEvictFirst : kEvictNormal;
     for (int t = first_tile; t < num_tiles; t += tile_step) {
-      const int mi = t % MT, ni = t / MT;
+      int mi, ni;
+      gemm_tile_coords(t, MT, NT, p.m_band, mi, ni);
       const int grp = (mi < mt0) ? 0 : 1;
       const int m0 = (grp ? mi - mt0 : mi) * Cfg::kTileM + int(cta_rank) * 128;
       const int n0 = ni * kBN + int(cta_rank) * Cfg::kBRows;
-      const CUtensorMap* tA = grp ? &tmA1 : &tmA0;
-      const CUtensorMap* tB = grp ? &tmB1 : &tmB0;
+      const CUtensorMap* tAm = grp ? &tmA1 : &tmA0;
+      const CUtensorMap* tAe = grp ? &tmE1 : &tmE0;
+      const CUtensorMap* tBm = grp ? &tmB1 : &tmB0;
+      const CUtensorMap* tBe = grp ? &tmF1 : &tmF0;
       for (int kb = 0; kb < KB; ++kb) {
         if constexpr (kCtaGroup == 2) mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
         else mbar_wait(&empty_bar[stage], phase ^ 1);
         if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCtaGroup);
         uint8_t* sa = smem_a + stage * Cfg::kABytes;
         uint8_t* sb = smem_b + stage * Cfg::kBBytes;
+        const CUtensorMap* tA = kb < KBm ? tAm : tAe;
+        const CUtensorMap* tB = kb < KBm ? tBm : tBe;
+        const int k_col = (kb < KBm ? kb : kb - KBm) * kGemmBlockK;
         if constexpr (kCtaGroup == 2) {
-          tma_load_2d_2sm(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, hint_a);
-          tma_load_2d_2sm(tB, &full_bar[stage], sb, kb * kGemmBlockK, n0, hint_b);
+          tma_load_2d_2sm(tA, &full_bar[stage], sa, k_col, m0, hint_a);
+          tma_load_2d_2sm(tB, &full_bar[stage], sb, k_col, n0, hint_b);
         } else {
-          tma_load_2d(tA, &full_bar[stage], sa, kb * kGemmBlockK, m0, hint_a);
-          tma_load_2d(tB, &full_bar[stage], sb, kb * kGemmBlockK, n0, hint_b);
+          tma_load_2d(tA, &full_bar[stage], sa, k_col, m0, hint_a);
+          tma_load_2d(tB, &full_bar[stage], sb, k_col, n0, hint_b);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -369,7 +404,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = first_tile; t < num_tiles; t += tile_step) {
-      const int mi = t % MT, ni = t / MT;
+      int mi, ni;
+      gemm_tile_coords(t, MT, NT, p.m_band, mi, ni);
       const int grp = (mi < mt0) ? 0 : 1;
       const int m_local = (grp ? mi - mt0 : mi) * Cfg::kTileM + int(cta_rank) * 128 + quad * 32 + lane;
       const int n_tile0 = ni * kBN;

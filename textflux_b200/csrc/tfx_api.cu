@@ -203,6 +203,8 @@ void configure_kernels(std::string* err_) {
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 224>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 192>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 192>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 64>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 64>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<256, 1>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<256, 2>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<224, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<224, 2>::kSmemBytes));
@@ -238,21 +240,27 @@ int pick_block_n(long long m_tiles, int N, int units, bool allow_narrow) {
   return (allow_narrow && c224 < c256) ? 224 : 256;
 }
 
+// Operands of the extension k-block (GemmParams::k_ext): A side [M, 64] per group, W side [N, 64] per group.
+struct GemmExt {
+  const CUtensorMap *e0, *e1, *f0, *f1;
+};
+
 template <int kCG, int kBN>
 void launch_gemm_inst(const LaunchCtx& c, long long tiles, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
-                      const CUtensorMap& b1, const GemmParams& p) {
+                      const CUtensorMap& b1, const GemmExt* x, const GemmParams& p) {
   std::string* err_ = c.err_;
   const int sms = num_sms(c.device);
   long long ctas = (kCG == 2) ? 2 * (tiles < sms / 2 ? tiles : sms / 2) : (tiles < sms ? tiles : sms);
   CUDA_TRY(launch_ex(gemm_tcgen05_kernel<kCG, kBN>, dim3((unsigned)ctas), dim3(kGemmThreads), GemmCfg<kCG, kBN>::kSmemBytes, c, kCG,
-                     a0, a1, b0, b1, p));
+                     a0, a1, b0, b1, x ? *x->e0 : a0, x ? *x->e1 : a1, x ? *x->f0 : b0, x ? *x->f1 : b1, p));
 }
 
 // b0/b1 must be descriptors whose box holds block_n / cta_group rows.
 void launch_gemm(const LaunchCtx& c, int cta_group, int block_n, const CUtensorMap& a0, const CUtensorMap& a1,
-                 const CUtensorMap& b0, const CUtensorMap& b1, const GemmParams& p) {
+                 const CUtensorMap& b0, const CUtensorMap& b1, const GemmParams& p, const GemmExt* ext = nullptr) {
   std::string* err_ = c.err_;
   REQUIRE(p.K % kGemmBlockK == 0 && p.K > 0, TFX_ERR_INVALID, "GEMM K=%d must be a positive multiple of %d", p.K, kGemmBlockK);
+  REQUIRE(p.k_ext == 0 || (p.k_ext == kGemmBlockK && ext), TFX_ERR_INVALID, "k_ext %d needs extension descriptors", p.k_ext);
   REQUIRE(p.n_split == p.N || p.n_split % block_n == 0, TFX_ERR_INVALID, "n_split %d not tile aligned", p.n_split);
   const bool qkv = p.mode0 == EPI_QKV || (p.n_split < p.N && p.mode1 == EPI_QKV);
   REQUIRE(!qkv || block_n == 256, TFX_ERR_INVALID, "QKV epilogue needs 256-wide tiles");
@@ -264,12 +272,14 @@ void launch_gemm(const LaunchCtx& c, int cta_group, int block_n, const CUtensorM
   if (tiles == 0) return;
   const int key = cta_group * 1000 + block_n;
   switch (key) {
-    case 1256: launch_gemm_inst<1, 256>(c, tiles, a0, a1, b0, b1, p); break;
-    case 2256: launch_gemm_inst<2, 256>(c, tiles, a0, a1, b0, b1, p); break;
-    case 1224: launch_gemm_inst<1, 224>(c, tiles, a0, a1, b0, b1, p); break;
-    case 2224: launch_gemm_inst<2, 224>(c, tiles, a0, a1, b0, b1, p); break;
-    case 1192: launch_gemm_inst<1, 192>(c, tiles, a0, a1, b0, b1, p); break;
-    case 2192: launch_gemm_inst<2, 192>(c, tiles, a0, a1, b0, b1, p); break;
+    case 1256: launch_gemm_inst<1, 256>(c, tiles, a0, a1, b0, b1, ext, p); break;
+    case 2256: launch_gemm_inst<2, 256>(c, tiles, a0, a1, b0, b1, ext, p); break;
+    case 1224: launch_gemm_inst<1, 224>(c, tiles, a0, a1, b0, b1, ext, p); break;
+    case 2224: launch_gemm_inst<2, 224>(c, tiles, a0, a1, b0, b1, ext, p); break;
+    case 1192: launch_gemm_inst<1, 192>(c, tiles, a0, a1, b0, b1, ext, p); break;
+    case 2192: launch_gemm_inst<2, 192>(c, tiles, a0, a1, b0, b1, ext, p); break;
+    case 1064: launch_gemm_inst<1, 64>(c, tiles, a0, a1, b0, b1, ext, p); break;
+    case 2064: launch_gemm_inst<2, 64>(c, tiles, a0, a1, b0, b1, ext, p); break;
     default: REQUIRE(false, TFX_ERR_INVALID, "no GEMM instance for cta_group %d block_n %d", cta_group, block_n);
   }
   ++*c.counter;
@@ -569,6 +579,8 @@ struct tfx_model {
                          // 8: schedule 4 (attention4.cuh): schedule 3 split-P + the last partial wave cut into KV shares;
                          // 9: schedule 5 (attention5.cuh): persistent CTAs, items overlapped, remainder cut into KV shares
   int gemm_narrow_tiles = 1;  // allow 224-wide tiles where they cut wave quantisation (option "gemm_narrow_tiles")
+  int gemm_m_band = -1;  // tile order of the wide-K GEMMs (ff down, single proj_out), whose A operand outgrows the L2 at N >= 4608:
+                         // 0 = M-fastest over all M tiles, b > 0 = bands of b M tiles (GemmParams::m_band), -1 = per shape (band_for)
   int gemm_l2_hints = 0;  // bit 0: A (activation) loads evict_last, bit 1: B (weight) loads evict_first (option "gemm_l2_hints")
   int attn_emu = 2;  // column pairs per 8 whose exponentials run on the FMA pipe (packed polynomial) instead of MUFU:
                      // 2 measured best (+4..8 %), 0 = all MUFU
@@ -600,6 +612,14 @@ struct tfx_model {
   enum AKind { A_NBUF = 0, A_ATTN = 1, A_MLP = 2, A_CAT = 3, A_X = 4, A_ENC = 5, A_KINDS = 6 };
   CUtensorMap mA[2][A_KINDS][2];  // [0: 128-row boxes | 1: 128/gemm_mcast-row boxes for the multicast kernels][kind][group]
   CUtensorMap mQ, mK, mV;  // [B*H, N, dh] with 128-row boxes
+  // unfused LoRA (side path): a packed matrix "<m>.w" with adapters registered as "<m>.la" [64, K] (the lora_A rows of the
+  // modules packed into it, zero padded) and "<m>.lb" [N, 64] ((alpha/r) * lora_B of each module in its rows x its columns)
+  // runs T = bf16(x la^T) into `tbuf`, then its GEMM with one extension k-block (T, lb): x W^T + T lb^T in one accumulator
+  bf16* tbuf = nullptr;      // [B*N, 64]
+  CUtensorMap mT[2];         // tbuf rows of the text / image group as the A extension
+  bf16* side_zero = nullptr;  // zeros: stands in for la / lb / the T bias on the stream of a launch that has no adapter
+  long long side_zero_elems = 0;
+  bool has_side = false;
   Attn4Workspace attn_ws;  // partial (O, m, l) of the KV shares of schedule 4
   std::map<std::string, CUtensorMap> mB;  // weight-side descriptors, keyed "<weight>#<cta_group>#<block_n>"
 
@@ -631,12 +651,39 @@ struct tfx_model {
     }
     return it->second;
   }
+  // descriptor over a side-path matrix ([rows, cols] bf16, or the zero block read as that shape)
+  const CUtensorMap& side_map(const std::string& name, long long rows, long long cols, int block_n, int cg) {
+    const std::string key = name + "#" + std::to_string(rows) + "x" + std::to_string(cols) + "#" + std::to_string(cg) + "#" + std::to_string(block_n);
+    auto it = mB.find(key);
+    if (it == mB.end()) {
+      const bf16* ptr = side_zero;
+      if (name != "side_zero") {
+        const Weight& t = W(name);
+        REQUIRE(t.rows == rows && t.cols == cols, TFX_ERR_INVALID, "side matrix '%s' is [%lld,%lld], expected [%lld,%lld]", name.c_str(),
+                t.rows, t.cols, rows, cols);
+        ptr = t.ptr;
+      } else {
+        REQUIRE(rows * cols <= side_zero_elems, TFX_ERR_STATE, "zero block too small for [%lld,%lld]", rows, cols);
+      }
+      it = mB.emplace(key, make_map_2d(err_, ptr, rows, cols, cols, block_n / cg)).first;
+    }
+    return it->second;
+  }
   // tile width for a two-stream (text rows + image rows) GEMM of width Nn
   int block_n_for(int Nn) const {
     const int tile_m = 128 * gemm_cta_group;
     const long long mt = ((long long)B * T + tile_m - 1) / tile_m + ((long long)B * S + tile_m - 1) / tile_m;
     const int bn = pick_block_n(mt, Nn, num_sms(device) / gemm_cta_group, gemm_narrow_tiles != 0);
     return (gemm_mcast >= 2 && bn == 192) ? 256 : bn;
+  }
+  // Wide-K GEMM [rows, K] x [Nn, K]^T: when A is larger than half the L2, walk it in bands of M tiles sized so that one band x all N
+  // tiles is one wave -- each wave then streams band x 256 rows of A once and the whole weight, instead of the whole of A.
+  // Measured in the step (profiles/r2h_band.md): cfg3 72.05 -> 71.4 ms, cfg5 142.0 -> 138.6 ms, DRAM traffic 81.6 -> 74.5 GB.
+  int band_for(long long rows, long long K, int Nn, int bn) const {
+    if (gemm_m_band >= 0) return gemm_m_band;
+    if (rows * K * 2 <= (64LL << 20)) return 0;
+    const int units = num_sms(device) / gemm_cta_group, nt = (Nn + bn - 1) / bn;
+    return std::max(1, units / nt);
   }
   void drop_graphs() {
     for (int i = 0; i < 4; ++i)
@@ -671,6 +718,30 @@ struct tfx_model {
   void gemm(const LaunchCtx& c, int bn, AKind kind, const std::string& w0, const std::string& w1, const GemmParams& p, int ga = -1) {
     const int g0 = ga < 0 ? 0 : ga, g1 = ga < 0 ? 1 : ga;
     const int nt = (p.N + bn - 1) / bn;
+    if (has_side && ga < 0) {
+      const std::string m0 = w0.substr(0, w0.size() - 2), m1 = w1.substr(0, w1.size() - 2);  // strip ".w"
+      const bool s0 = w.count(m0 + ".la") != 0, s1 = w.count(m1 + ".la") != 0;
+      if (s0 || s1) {
+        const int cg = gemm_cta_group;
+        const std::string z = "side_zero";
+        // T = bf16(x la^T): [rows, 64] per group (a group without adapters multiplies by zeros: its extension adds nothing)
+        GemmParams pt;
+        memset(&pt, 0, sizeof pt);
+        pt.N = 64; pt.K = p.K; pt.num_groups = 2; pt.n_split = 64; pt.mode0 = pt.mode1 = EPI_STORE;
+        for (int g = 0; g < 2; ++g) {
+          pt.g[g].M = p.g[g].M; pt.g[g].rows_per_sample = p.g[g].rows_per_sample;
+          pt.g[g].bias = side_zero; pt.g[g].out = tbuf + (g ? (long long)p.g[0].M * 64 : 0); pt.g[g].ldo = 64;
+        }
+        // single-CTA 128 x 64 tiles: the output is one tile wide, so the M tiles are all the parallelism there is
+        launch_gemm(c, 1, 64, mA[0][kind][0], mA[0][kind][1], side_map(s0 ? m0 + ".la" : z, 64, p.K, 64, 1),
+                    side_map(s1 ? m1 + ".la" : z, 64, p.K, 64, 1), pt);
+        GemmParams pe = p;
+        pe.k_ext = kGemmBlockK;
+        GemmExt x{&mT[0], &mT[1], &side_map(s0 ? m0 + ".lb" : z, p.N, 64, bn, cg), &side_map(s1 ? m1 + ".lb" : z, p.N, 64, bn, cg)};
+        launch_gemm(c, cg, bn, mA[0][kind][0], mA[0][kind][1], WB(w0, bn, cg), WB(w1, bn, cg), pe, &x);
+        return;
+      }
+    }
     if (gemm_mcast >= 2 && nt >= gemm_mcast) {
       launch_gemm_mc(c, gemm_mcast, bn, mA[1][kind][g0], mA[1][kind][g1], WB(w0, bn, 2), WB(w1, bn, 2), p);
     } else {
@@ -718,6 +789,7 @@ void tfx_model::prepare(int B_, int S_, int T_) {
   lat_in = alloc<bf16>((long long)B * S * cfg.out_channels);
   lat_out = alloc<bf16>((long long)B * S * cfg.out_channels);
   rope = alloc<float2>((long long)N * (dh / 2));
+  tbuf = alloc<bf16>(R * 64);
   CUDA_TRY(cudaMemset(cat, 0, R * 5 * D * sizeof(bf16)));
   mc_ready = false;
   if (mod_cache_slots > 0) {
@@ -748,6 +820,8 @@ void tfx_model::prepare(int B_, int S_, int T_) {
       mA[vi][A_ENC][g] = make_map_2d(err_, enc_in, rt, cfg.joint_attention_dim, cfg.joint_attention_dim, box);
     }
   }
+  mT[0] = make_map_2d(err_, tbuf, rt, 64, 64, 128);
+  mT[1] = make_map_2d(err_, tbuf + rt * 64, ri, 64, 64, 128);
   mQ = make_map_3d(err_, q, (long long)B * H, N, dh);
   mK = make_map_3d(err_, k, (long long)B * H, N, dh);
   mV = make_map_3d(err_, v, (long long)B * H, N, dh);
@@ -910,6 +984,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].out = hid_g[g]; p.g[g].ldo = D; p.g[g].res = hid_g[g]; p.g[g].ldr = D;
         p.g[g].gate = mod + mod_double(i, g == 0, 5); p.g[g].gate_stride = mod_rows;
       }
+      p.m_band = band_for(rt + ri, 4LL * D, D, bn_d);
       gemm(c, bn_d, A_MLP, name("d%d.ff2_c", i, ".w"), name("d%d.ff2_x", i, ".w"), p);
     }
   }
@@ -943,6 +1018,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].gate = mod + mod_single(j, 2); p.g[g].gate_stride = mod_rows;
       }
       const std::string wn = name("s%d.out", j, ".w");
+      p.m_band = band_for(rt + ri, 5LL * D, D, bn_d);
       gemm(c, bn_d, A_CAT, wn, wn, p);
     }
   }
@@ -1065,6 +1141,7 @@ void tfx_destroy(tfx_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   h->free_workspace();
+  if (h->side_zero) cudaFree(h->side_zero);
   cudaEventDestroy(h->ev_in);
   cudaEventDestroy(h->ev_out);
   cudaStreamDestroy(h->stream);
@@ -1090,6 +1167,9 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
     h->attn_emu = (int)value;
   } else if (k == "gemm_narrow_tiles") {
     h->gemm_narrow_tiles = value != 0;  // weight-side descriptors are keyed by tile width: nothing to rebuild
+  } else if (k == "gemm_m_band") {
+    REQUIRE(value >= -1 && value <= 64, TFX_ERR_INVALID, "gemm_m_band must be -1 (per shape) or 0..64");
+    h->gemm_m_band = (int)value;
   } else if (k == "gemm_l2_hints") {
     REQUIRE(value >= 0 && value <= 3, TFX_ERR_INVALID, "gemm_l2_hints must be 0..3");
     h->gemm_l2_hints = (int)value;
@@ -1188,8 +1268,35 @@ int tfx_finalize_weights(tfx_handle h) {
     lin(p + "qkvmlp", 7 * D, D); lin(p + "out", D, 5 * D);
     need(p + "rms_q", 1, h->dh); need(p + "rms_k", 1, h->dh);
   }
+  // unfused-LoRA side matrices: "<m>.la" [64, K] and "<m>.lb" [N, 64] next to a packed "<m>.w" [N, K], always as a pair
+  h->has_side = false;
+  for (const auto& kv : h->w) {
+    const std::string& n = kv.first;
+    if (n.size() < 3) continue;
+    const std::string sfx = n.substr(n.size() - 3), m = n.substr(0, n.size() - 3);
+    if (sfx != ".la" && sfx != ".lb") continue;
+    REQUIRE(h->w.count(m + ".w") && h->w.count(m + ".la") && h->w.count(m + ".lb"), TFX_ERR_MISSING,
+            "side adapter '%s' needs '%s.w', '%s.la' and '%s.lb'", n.c_str(), m.c_str(), m.c_str(), m.c_str());
+    const Weight& base = h->W(m + ".w");
+    if (sfx == ".la") need(n, 64, base.cols); else need(n, base.rows, 64);
+    h->has_side = true;
+  }
+  if (h->has_side && !h->side_zero) {
+    h->side_zero_elems = 64LL * 7 * D;
+    CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&h->side_zero), (size_t)h->side_zero_elems * 2));
+    CUDA_TRY(cudaMemset(h->side_zero, 0, (size_t)h->side_zero_elems * 2));
+  }
   h->build_weight_maps();
+  h->drop_graphs();  // the launch sequence depends on which matrices carry side adapters
   h->finalized = true;
+  API_END
+}
+
+int tfx_unset_weight(tfx_handle h, const char* name) {
+  API_BEGIN(h)
+  REQUIRE(h && name, TFX_ERR_INVALID, "null argument");
+  h->w.erase(name);
+  h->finalized = false;
   API_END
 }
 
@@ -1419,6 +1526,63 @@ int tfx_op_linear(const void* A, int64_t lda, const void* Wt, const void* bias, 
     LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
     if (pn) launch_gemm_mc(c, pn, bn, ma, ma, mb, mb, p);
     else launch_gemm(c, cta_group, bn, ma, ma, mb, mb, p);
+  } catch (const Fail& f) {
+    return f.code;
+  }
+  return TFX_OK;
+}
+
+int tfx_op_linear_lora(const void* A, int64_t lda, const void* Wt, const void* bias, const void* la, const void* lb, void* t_scratch,
+                       void* out, int64_t ldo, int32_t M, int32_t N, int32_t K, int32_t mode, const void* gate, const void* res,
+                       int32_t cta_group, int32_t m_band, void* stream) {
+  std::string* err_ = nullptr;
+  try {
+    REQUIRE(A && Wt && bias && out, TFX_ERR_INVALID, "null argument");
+    REQUIRE((la == nullptr) == (lb == nullptr) && (!la || t_scratch), TFX_ERR_INVALID, "la, lb and t_scratch go together");
+    REQUIRE(mode >= 0 && mode <= 2, TFX_ERR_INVALID, "mode must be 0..2");
+    REQUIRE(cta_group == 1 || cta_group == 2, TFX_ERR_INVALID, "cta_group must be 1 or 2");
+    REQUIRE(mode != EPI_GATE_RES || (gate && res), TFX_ERR_INVALID, "gate/res required for mode 2");
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    configure_kernels(err_);
+    if (M == 0) return TFX_OK;
+    const int cg = cta_group;
+    const char* force = getenv("TFX_OP_LINEAR_BLOCK_N");
+    const int bn = force ? atoi(force) : pick_block_n((M + 128 * cg - 1) / (128 * cg), N, num_sms(dev) / cg, true);
+    REQUIRE(bn == 256 || bn == 224 || bn == 192, TFX_ERR_INVALID, "TFX_OP_LINEAR_BLOCK_N must be 256, 224 or 192");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    LaunchCtx c{st, dev, &g_op_launches, err_};
+    CUtensorMap ma = make_map_2d(err_, A, M, K, lda, 128);
+    CUtensorMap mb = make_map_2d(err_, Wt, N, K, K, bn / cg);
+    GemmParams p;
+    memset(&p, 0, sizeof p);
+    p.N = N; p.K = K; p.num_groups = 1; p.n_split = N; p.mode0 = mode; p.mode1 = mode; p.m_band = m_band;
+    p.g[0].M = M; p.g[0].rows_per_sample = M; p.g[0].bias = reinterpret_cast<const bf16*>(bias);
+    p.g[0].out = reinterpret_cast<bf16*>(out); p.g[0].ldo = ldo;
+    p.g[0].res = reinterpret_cast<const bf16*>(res); p.g[0].ldr = ldo;
+    p.g[0].gate = reinterpret_cast<const bf16*>(gate); p.g[0].gate_stride = 0;
+    if (!la) {
+      launch_gemm(c, cg, bn, ma, ma, mb, mb, p);
+      return TFX_OK;
+    }
+    static std::map<int, bf16*> zero_on;  // per device: 64 zeros, the bias of the T GEMM
+    bf16*& zero = zero_on[dev];
+    if (!zero) {
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&zero), 256));
+      CUDA_TRY(cudaMemset(zero, 0, 256));
+    }
+    CUtensorMap mla = make_map_2d(err_, la, 64, K, K, 64);
+    GemmParams pt;
+    memset(&pt, 0, sizeof pt);
+    pt.N = 64; pt.K = K; pt.num_groups = 1; pt.n_split = 64; pt.mode0 = pt.mode1 = EPI_STORE;
+    pt.g[0].M = M; pt.g[0].rows_per_sample = M; pt.g[0].bias = zero;
+    pt.g[0].out = reinterpret_cast<bf16*>(t_scratch); pt.g[0].ldo = 64;
+    launch_gemm(c, 1, 64, ma, ma, mla, mla, pt);
+    CUtensorMap mt = make_map_2d(err_, t_scratch, M, 64, 64, 128);
+    CUtensorMap mlb = make_map_2d(err_, lb, N, 64, 64, bn / cg);
+    p.k_ext = kGemmBlockK;
+    GemmExt x{&mt, &mt, &mlb, &mlb};
+    launch_gemm(c, cg, bn, ma, ma, mb, mb, p, &x);
   } catch (const Fail& f) {
     return f.code;
   }

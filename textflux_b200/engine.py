@@ -98,6 +98,7 @@ class B200FluxTransformer(torch.nn.Module):
         self._shape: Optional[Tuple[int, int, int]] = None
         folded = getattr(get, "lora_modules", None) if lora_modules is None else lora_modules
         self._lora_modules: set = set(folded or ())
+        self._side: Dict[str, Tensor] = {}  # side matrices of an unfused adapter ("<packed>.la" / ".lb"), kept alive here
         self.set_option("use_graph", int(use_graph))
         if gemm_mcast is not None:
             self.set_option("gemm_mcast", gemm_mcast)
@@ -140,26 +141,63 @@ class B200FluxTransformer(torch.nn.Module):
         return cls(config, state_dict.__getitem__, device=device, **kw)
 
     # ---- LoRA hot-swap (loaders/lora_pipeline.py: load_lora_weights / unload_lora_weights) ------------------------
-    def load_lora_weights(self, get_base: Callable[[str], Tensor], lora: Dict[str, Tensor], scale: float = 1.0) -> None:
-        """Fold an adapter into the packed weights in place, replacing any adapter folded before.  `get_base(name)` returns
-        the BASE tensor of the reference state dict (e.g. `loader.Checkpoint(path).getter(device)` or
-        `module.state_dict().__getitem__`); only the packed matrices that contain a module touched by the old or the new
-        adapter are rewritten (W + scale * alpha/r * B A in fp32, as at load), every device pointer, TMA descriptor and the
-        captured step graph stay valid."""
-        from .packer import fold_lora, lora_modules, repack_modules
-        mods = set(lora_modules(lora)) | self._lora_modules
+    def load_lora_weights(self, get_base: Callable[[str], Tensor], lora: Dict[str, Tensor], scale: float = 1.0,
+                          mode: str = "fold", side_threshold: float = 0.05) -> Dict[str, str]:
+        """Install an adapter on the live engine, replacing any adapter installed before.  `get_base(name)` returns the BASE
+        tensor of the reference state dict (e.g. `loader.Checkpoint(path).getter(device)` or `module.state_dict().__getitem__`).
+
+        mode "fold": W + scale * alpha/r * B A in fp32 -> bf16, written in place into the packed matrices that hold a touched
+        module (every device pointer, TMA descriptor and the captured step graph stay valid) -- free at run time.
+        mode "side": the reference's own unfused form (run_inference_lora.py:52-65): the base weights stay, each touched packed
+        GEMM gains one extension k-block computing `+ bf16(x A^T) (scale * alpha/r * B)^T` in the same accumulator (~3 % step time).
+        mode "auto": per packed matrix, measured (`packer.fold_noise`): fold where the bf16 fold keeps the adapter to within
+        `side_threshold` of its own norm, side path where the delta is too close to W's bf16 ulp for that.
+        Returns {packed name: "fold" | "side"}."""
+        from .packer import fold_lora, fold_noise, lora_modules, packed_layout, repack_modules, side_lora
+        if mode not in ("fold", "side", "auto"):
+            raise ValueError(f"mode must be 'fold', 'side' or 'auto', not {mode!r}")
+        cfg = SimpleNamespace(**self.config)
+        new_mods = set(lora_modules(lora))
+        holders = {name: [r for r in refs if r in new_mods] for name, kind, refs in packed_layout(cfg) if kind == "lin"}
+        holders = {n: r for n, r in holders.items() if r}
+        if mode == "auto":
+            noise = fold_noise(cfg, get_base, lora, scale=scale, device=self._dev)
+            plan = {n: ("side" if noise[n] > side_threshold else "fold") for n in holders}
+        else:
+            plan = {n: mode for n in holders}
+        fold_mods = {r for n, refs in holders.items() if plan[n] == "fold" for r in refs}
         with torch.cuda.device(self._dev):
-            repack_modules(SimpleNamespace(**self.config), fold_lora(get_base, lora, scale=scale), self._weights, mods)
+            # modules folded before go back to base unless folded again; modules folded now get W + delta
+            restore = (self._lora_modules | fold_mods)
+            if restore:
+                sub = {k: v for k, v in lora.items() if any(k.startswith(p + m + ".") for m in fold_mods for p in ("transformer.", ""))}
+                repack_modules(cfg, fold_lora(get_base, sub, scale=scale) if sub else get_base, self._weights, restore)
+            had_side = bool(self._side)
+            for name in list(self._side):
+                _lib.check(self._lib.tfx_unset_weight(self._h, name.encode()), self._h)
+            self._side = side_lora(cfg, lora, self._dev, scale=scale, only=[n for n in holders if plan[n] == "side"])
+            for name, t in self._side.items():
+                _lib.check(self._lib.tfx_set_weight(self._h, name.encode(), t.data_ptr(), t.shape[0], t.shape[1]), self._h)
             torch.cuda.current_stream(self._dev).synchronize()
-        self._lora_modules = set(lora_modules(lora))
+            if had_side or self._side:  # a fold-only swap changes values in place: descriptors and the step graph stay
+                _lib.check(self._lib.tfx_finalize_weights(self._h), self._h)
+        self._lora_modules = fold_mods
         self.set_option("mod_cache_reset", 1)  # modulation vectors cached from the old weights must not be served again
+        return plan
 
     def unload_lora_weights(self, get_base: Callable[[str], Tensor]) -> None:
-        """Restore the base weights of every module the current adapter touched."""
+        """Restore the base weights of every module the current adapter touched and drop its side matrices."""
         from .packer import repack_modules
         with torch.cuda.device(self._dev):
-            repack_modules(SimpleNamespace(**self.config), get_base, self._weights, self._lora_modules)
+            if self._lora_modules:
+                repack_modules(SimpleNamespace(**self.config), get_base, self._weights, self._lora_modules)
+            had_side = bool(self._side)
+            for name in list(self._side):
+                _lib.check(self._lib.tfx_unset_weight(self._h, name.encode()), self._h)
+            self._side = {}
             torch.cuda.current_stream(self._dev).synchronize()
+            if had_side:
+                _lib.check(self._lib.tfx_finalize_weights(self._h), self._h)
         self._lora_modules = set()
         self.set_option("mod_cache_reset", 1)
 

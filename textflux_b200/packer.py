@@ -196,6 +196,87 @@ def fold_lora(get: Callable[[str], Tensor], lora: Dict[str, Tensor], scale: floa
     return wrapped
 
 
+SIDE_RANK = 64  # columns of the GEMM's extension k-block: the ranks of the modules packed into one matrix must fit
+
+
+def _lora_index(lora: Dict[str, Tensor], prefix: str) -> Dict[str, str]:
+    mods = {}
+    for k in lora:
+        if k.endswith(".lora_A.weight"):
+            m = k[: -len(".lora_A.weight")]
+            mods[m[len(prefix):] if m.startswith(prefix) else m] = m
+    return mods
+
+
+def _lora_factor(lora: Dict[str, Tensor], m: str, scale: float) -> float:
+    r = lora[m + ".lora_A.weight"].shape[0]
+    alpha = float(lora[m + ".alpha"]) if (m + ".alpha") in lora else float(r)
+    return scale * alpha / r
+
+
+def side_lora(cfg, lora: Dict[str, Tensor], device, scale: float = 1.0, prefix: str = "transformer.",
+              only: Optional[Iterable[str]] = None, dtype=torch.bfloat16) -> Dict[str, Tensor]:
+    """The adapter in the layout of the engine's UNFUSED path (include/textflux_b200.h, tfx_set_weight): for every packed
+    matrix `<p>.w` [N, K] that holds an adapted module, `<p>.la` [64, K] = the modules' lora_A stacked (rank rows each, zero
+    padded to 64) and `<p>.lb` [N, 64] = scale * alpha/r * lora_B of each module in that module's rows and rank columns.
+    The packed GEMM then computes x W^T + bf16(x la^T) lb^T -- PEFT's `base(x) + scaling * lora_B(lora_A(x))`
+    (run_inference_lora.py:52-65 keeps adapters unfused) -- and the base weight stays untouched.  `only`: packed names to build."""
+    mods = _lora_index(lora, prefix)
+    shapes = dict(reference_names(cfg))
+    only = None if only is None else set(only)
+    out: Dict[str, Tensor] = {}
+    for name, kind, refs in packed_layout(cfg):
+        if kind != "lin" or not any(r in mods for r in refs) or (only is not None and name not in only):
+            continue
+        N = sum(shapes[r + ".weight"][0] for r in refs)
+        K = shapes[refs[0] + ".weight"][1]
+        la = torch.zeros(SIDE_RANK, K, device=device, dtype=dtype)
+        lb = torch.zeros(N, SIDE_RANK, device=device, dtype=dtype)
+        row = col = 0
+        for r in refs:
+            o = shapes[r + ".weight"][0]
+            if r in mods:
+                A, Bm = lora[mods[r] + ".lora_A.weight"], lora[mods[r] + ".lora_B.weight"]
+                rk = A.shape[0]
+                if col + rk > SIDE_RANK:
+                    raise ValueError(f"textflux_b200: the adapters packed into '{name}' have total rank {col + rk} > {SIDE_RANK}; "
+                                     f"use the folded path for it")
+                la[col:col + rk].copy_(A.to(device=device, dtype=dtype))
+                lb[row:row + o, col:col + rk].copy_((Bm.to(device=device, dtype=torch.float32) * _lora_factor(lora, mods[r], scale)).to(dtype))
+                col += rk
+            row += o
+        out[name + ".la"], out[name + ".lb"] = la, lb
+    return out
+
+
+def fold_noise(cfg, get: Callable[[str], Tensor], lora: Dict[str, Tensor], scale: float = 1.0, prefix: str = "transformer.",
+               device=None) -> Dict[str, float]:
+    """How much of an adapter a bf16 fold loses, measured: per packed matrix, the largest
+    || (bf16(W + d) - W) - d ||_F / || d ||_F over its adapted modules, d = scale * alpha/r * B A in fp32.  Near 0 the fold realises
+    the adapter; it grows as d shrinks towards W's bf16 ulp, where the unfused side path should be used."""
+    mods = _lora_index(lora, prefix)
+    out: Dict[str, float] = {}
+    for name, kind, refs in packed_layout(cfg):
+        if kind != "lin":
+            continue
+        worst = None
+        for r in refs:
+            if r not in mods:
+                continue
+            w = get(r + ".weight")
+            dev = device or w.device
+            w32 = w.to(device=dev, dtype=torch.float32)
+            A = lora[mods[r] + ".lora_A.weight"].to(device=dev, dtype=torch.float32)
+            Bm = lora[mods[r] + ".lora_B.weight"].to(device=dev, dtype=torch.float32)
+            d = _lora_factor(lora, mods[r], scale) * (Bm @ A)
+            folded = (w32 + d).to(torch.bfloat16).to(torch.float32)
+            e = float(((folded - w32) - d).norm() / d.norm().clamp_min(1e-30))
+            worst = e if worst is None else max(worst, e)
+        if worst is not None:
+            out[name] = worst
+    return out
+
+
 def synthetic_getter(cfg, seed: int, device, dtype=torch.bfloat16, w_std=0.02, b_std=0.02, rms_std=0.1):
     """Random weights of the reference's shapes generated on `device`, one tensor at a time (bench / smoke use: there
     is no network for real checkpoints).  N(0, 0.02^2) linears, RMSNorm weights 1 + N(0, 0.1^2)."""

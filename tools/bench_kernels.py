@@ -79,6 +79,33 @@ def main():
         print(row, flush=True)
         res.append(row)
         del A, W, out
+    # tile order (GemmParams::m_band) on the wide-K GEMMs, and the cost of the unfused-LoRA side path
+    band_shapes = [(5120, 3072, 15360, "single proj_out cfg3"), (5120, 3072, 12288, "ff down cfg3"), (8704, 3072, 15360, "single proj_out cfg5"),
+                   (2560, 3072, 15360, "single proj_out cfg2"), (5120, 9216, 3072, "qkv cfg3"), (5120, 12288, 3072, "ff up cfg3")]
+    for M, N, K, name in (band_shapes if args.only in ("", "band") else []):
+        A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+        W = (torch.randn(N, K, device="cuda") * 0.02).to(torch.bfloat16)
+        b = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        la = (torch.randn(64, K, device="cuda") * 0.02).to(torch.bfloat16)
+        lb = (torch.randn(N, 64, device="cuda") * 0.02).to(torch.bfloat16)
+        tt = torch.empty(M, 64, device="cuda", dtype=torch.bfloat16)
+        row = {"kernel": "gemm_band", "name": name, "M": M, "N": N, "K": K}
+        for band in (0, 2, 3, 4, 5, 6, 8, 10):
+            def f():
+                _lib.check(lib.tfx_op_linear_lora(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), None, None, None, out.data_ptr(), N, M, N, K, 0,
+                                                  None, None, 2, band, st))
+            ms = timeit(f, flush=flush)
+            row[f"band{band}_tflops"] = 2.0 * M * N * K / ms / 1e9
+        def f():
+            _lib.check(lib.tfx_op_linear_lora(A.data_ptr(), K, W.data_ptr(), b.data_ptr(), la.data_ptr(), lb.data_ptr(), tt.data_ptr(),
+                                              out.data_ptr(), N, M, N, K, 0, None, None, 2, 0, st))
+        ms = timeit(f, flush=flush)
+        row["side_lora_tflops"] = 2.0 * M * N * K / ms / 1e9
+        row["side_lora_ms"] = ms
+        print(row, flush=True)
+        res.append(row)
+        del A, W, out
     for (T, S) in ([] if args.only not in ("", "attention") else [(512, 2048), (512, 4096), (512, 4608), (512, 8192), (512, 12288)]):
         H, dh, N = 24, 128, T + S
         q = torch.randn(1, H, N, dh, device="cuda").to(torch.bfloat16)
@@ -98,7 +125,7 @@ def main():
         row["sdpa_tflops"] = fl / ms / 1e9
         print(row, flush=True)
         res.append(row)
-    for rows, D in [(2560, 3072), (5120, 3072)]:
+    for rows, D in ([] if args.only not in ("", "ln") else [(2560, 3072), (5120, 3072)]):
         x = torch.randn(rows, D, device="cuda").to(torch.bfloat16)
         y = torch.empty_like(x)
         mod = torch.randn(1, 3 * D, device="cuda").to(torch.bfloat16)
@@ -108,7 +135,7 @@ def main():
         row = {"kernel": "ln_modulate", "rows": rows, "D": D, "us": ms * 1e3, "GBps": 2 * rows * D * 2 / ms / 1e6}
         print(row, flush=True)
         res.append(row)
-    if True:
+    if args.only in ("", "gemv"):
         Nn, K = 344 * 3072, 3072
         W = (torch.randn(Nn, K, device="cuda") * 0.02).to(torch.bfloat16)
         b = torch.zeros(Nn, device="cuda", dtype=torch.bfloat16)

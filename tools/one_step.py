@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--workload", default=bench.HEADLINE)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--attn-variant", type=int, default=-1)
+    ap.add_argument("--m-band", type=int, default=-1)
     args = ap.parse_args()
     from textflux_b200 import B200FluxTransformer, synthetic_getter
     from textflux_b200.engine import FrozenConfig
@@ -26,6 +27,8 @@ def main():
     eng = B200FluxTransformer(cfg, synthetic_getter(cfg, 1234, dev), device=dev)
     if args.attn_variant >= 0:
         eng.set_option("attn_variant", args.attn_variant)
+    if args.m_band >= 0:
+        eng.set_option("gemm_m_band", args.m_band)
     inp = bench.Inputs(args.workload, dev, 0, 1)
     eng.set_schedule(inp.ts, inp.guidance, inp.pooled_b, inp.S, inp.T)
     lat = inp.latents0
