@@ -180,6 +180,45 @@ int tfx_op_pack_mask(const void* mask, int32_t mask_is_f32, void* dst, int64_t d
 int tfx_op_umma_probe(const void* A, const void* Bm, void* D_f32, int32_t n_dim, int32_t k_dim, int32_t b_mn_major,
                       int32_t a_from_tmem, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep_bytes, void* stream);
 
+/* ---- AutoencoderKL: vae.encode at pipeline_flux_fill.py:1528, vae.decode at :2128 ------------------- */
+typedef struct tfx_vae* tfx_vae_handle;
+
+/* Mirrors AutoencoderKL.__init__'s @register_to_config arguments (models/autoencoders/autoencoder_kl.py:76-97) for the
+ * DownEncoderBlock2D / UpDecoderBlock2D family with act_fn = "silu" and no quant / post-quant convolutions (FLUX's VAE). */
+typedef struct {
+  int32_t in_channels;      /* 3 */
+  int32_t out_channels;     /* 3 */
+  int32_t latent_channels;  /* 16 */
+  int32_t num_blocks;       /* len(block_out_channels), 4 */
+  int32_t block_out_channels[8]; /* (128, 256, 512, 512) */
+  int32_t layers_per_block; /* 2 */
+  int32_t norm_num_groups;  /* 32 */
+  int32_t mid_block_add_attention;
+} tfx_vae_config;
+
+/* replaces AutoencoderKL.__init__ */
+int tfx_vae_create(const tfx_vae_config* cfg, int32_t device, tfx_vae_handle* out);
+void tfx_vae_destroy(tfx_vae_handle h);
+const char* tfx_vae_last_error(tfx_vae_handle h);
+/* "launches": kernels launched by this handle */
+int tfx_vae_get_counter(tfx_vae_handle h, const char* key, int64_t* value);
+/* Registers a bf16 device tensor under its reference state-dict name (replaces load_state_dict).  Layouts: 3x3 convolutions
+ * `<name>.weight` [Cout, 9 * Cin64] with column (ky * 3 + kx) * Cin64 + c, Cin64 = Cin rounded up to 64 (zero padded); 1x1
+ * convolutions and Linear layers [Cout, Cin]; biases and GroupNorm weight / bias [1, C].  INTEGRATION.md lists the names. */
+int tfx_vae_set_weight(tfx_vae_handle h, const char* name, const void* dev_ptr, int64_t rows, int64_t cols);
+/* replaces AutoencoderKL.encode up to the distribution parameters (autoencoder_kl.py:240-272 -> Encoder.forward, vae.py:140-193):
+ * image [B, in_channels, H, W] (fp32 or bf16, NCHW) -> moments [B, 2 * latent_channels, H / f, W / f] bf16 (mean ; logvar),
+ * f = 2^(num_blocks - 1).  DiagonalGaussianDistribution.sample / .mode stay with the caller (they draw from torch's generator). */
+int tfx_vae_encode(tfx_vae_handle h, const void* image, int32_t image_is_f32, int32_t B, int32_t H, int32_t W, void* moments_out,
+                   void* stream);
+/* replaces AutoencoderKL.decode (autoencoder_kl.py:274-324 -> Decoder.forward, vae.py:284-343): latents [B, latent_channels, h, w]
+ * bf16 -> image [B, out_channels, h * f, w * f] bf16 */
+int tfx_vae_decode(tfx_vae_handle h, const void* latents, int32_t B, int32_t h_latent, int32_t w_latent, void* image_out, void* stream);
+/* replaces DiagonalGaussianDistribution.sample (models/autoencoders/vae.py:793-803) once the caller has drawn `noise` from torch's
+ * generator where the reference draws it: out = bf16(mean + bf16(bf16(exp(bf16(0.5 * clamp(logvar, -30, 20)))) * noise)),
+ * moments [B, 2 * latent_channels, hw] bf16 (mean ; logvar), noise / out [B, latent_channels, hw] bf16 */
+int tfx_op_gaussian_sample(const void* moments, const void* noise, void* out, int32_t B, int32_t latent_channels, int64_t hw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

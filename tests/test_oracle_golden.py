@@ -1,8 +1,13 @@
 """CPU: the oracle restatement reproduces the committed reference outputs (tests/golden/, made by
 oracle/make_golden.py from the real reference) BIT-EXACTLY."""
+import os
+
+import pytest
 import torch
 
 from oracle import flux_oracle as fo
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _cfg(d):
@@ -146,3 +151,20 @@ def test_conditioning_glue_matches_reference_golden(golden):
 def test_flop_model_matches_survey():
     for S, tf in [(2048, 37.6650989568), (4608, 84.49265762304), (8192, 165.474467315712)]:
         assert abs(fo.flops_per_step(fo.FLUX_FILL_12B, S, 512) / 1e12 - tf) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- AutoencoderKL oracle
+@pytest.mark.parametrize("name", ["vae_small", "vae_flux"])
+def test_vae_oracle_matches_reference_golden(name):
+    """oracle/vae_oracle.py restates AutoencoderKL encode / decode bit-exactly (fixtures written by the real reference modules)."""
+    from oracle import vae_oracle as vo
+    d = torch.load(os.path.join(GOLDEN, name + ".pt"))
+    cfg = vo.VaeConfig(**{k: (tuple(v) if isinstance(v, list) else v) for k, v in d["config"].items()})
+    sd32 = vo.init_state_dict(cfg, seed=d["seed"])
+    for dtype, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        sd = {k: v.to(dtype) for k, v in sd32.items()}
+        m = vo.encode_moments(sd, cfg, d["image"].to(dtype))
+        assert torch.equal(m, d[f"moments_{tag}"])
+        assert torch.equal(vo.decode(sd, cfg, d["z"].to(dtype)), d[f"decoded_{tag}"])
+        noise = torch.randn(d[f"sample_{tag}"].shape, generator=torch.Generator().manual_seed(5), dtype=dtype)
+        assert torch.equal(vo.gaussian_sample(m, noise), d[f"sample_{tag}"])

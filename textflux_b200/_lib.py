@@ -8,6 +8,12 @@ import os
 from .build import LIB_PATH
 
 
+class TfxVaeConfig(C.Structure):
+    _fields_ = [("in_channels", C.c_int32), ("out_channels", C.c_int32), ("latent_channels", C.c_int32), ("num_blocks", C.c_int32),
+                ("block_out_channels", C.c_int32 * 8), ("layers_per_block", C.c_int32), ("norm_num_groups", C.c_int32),
+                ("mid_block_add_attention", C.c_int32)]
+
+
 class TfxConfig(C.Structure):
     _fields_ = [("in_channels", C.c_int32), ("out_channels", C.c_int32), ("num_layers", C.c_int32),
                 ("num_single_layers", C.c_int32), ("attention_head_dim", C.c_int32),
@@ -49,6 +55,14 @@ SIGNATURES = {
     "tfx_op_pack_latents": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _I32, _I32, C.c_float, C.c_float, _P]),
     "tfx_op_unpack_latents": (C.c_int, [_P, _I64, _P, _I32, _I32, _I32, _I32, _I32, C.c_float, C.c_float, _P]),
     "tfx_op_pack_mask": (C.c_int, [_P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _I32, _P]),
+    "tfx_vae_create": (C.c_int, [C.POINTER(TfxVaeConfig), _I32, C.POINTER(_P)]),
+    "tfx_vae_destroy": (None, [_P]),
+    "tfx_vae_last_error": (C.c_char_p, [_P]),
+    "tfx_vae_get_counter": (C.c_int, [_P, C.c_char_p, C.POINTER(_I64)]),
+    "tfx_vae_set_weight": (C.c_int, [_P, C.c_char_p, _P, _I64, _I64]),
+    "tfx_vae_encode": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "tfx_vae_decode": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    "tfx_op_gaussian_sample": (C.c_int, [_P, _P, _P, _I32, _I32, _I64, _P]),
     "tfx_op_umma_probe": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _U32, _U32, _U32, _P]),
 }
 
@@ -79,9 +93,9 @@ class TfxError(RuntimeError):
         self.code = code
 
 
-def check(code: int, handle=None):
+def check(code: int, handle=None, vae: bool = False):
     if code != 0:
-        msg = load().tfx_last_error(handle)
+        msg = load().tfx_vae_last_error(handle) if vae else load().tfx_last_error(handle)
         text = msg.decode() if msg else "unknown error"
         if code == 1:
             raise ValueError(f"textflux_b200: {text}")  # the reference raises ValueError on bad inputs

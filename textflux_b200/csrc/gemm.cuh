@@ -23,6 +23,7 @@ namespace tfx {
 
 enum EpiMode : int {
   EPI_STORE = 0,     // out = bf16(acc + bias)
+  EPI_STORE_F32 = 5,  // out (float*, ldo in floats) = acc, no bias: attention scores of the VAE mid block, kept in fp32 for the softmax
   EPI_GELU = 1,      // out = bf16(gelu_tanh(bf16(acc + bias)))
   EPI_GATE_RES = 2,  // out = bf16(res + bf16(gate * bf16(acc + bias)))
   EPI_QKV = 3,       // per-head RMSNorm + RoPE on q,k; scatter q,k,v head-major into the joint [text;image] buffers
@@ -45,6 +46,18 @@ struct GemmGroup {
   __nv_bfloat16* out2;  // EULER: latents out
 };
 
+// Implicit-GEMM 3x3 convolution over an NHWC bf16 image (AutoencoderKL: models/resnet.py ResnetBlock2D.conv1/conv2,
+// models/downsampling.py Downsample2D, models/upsampling.py Upsample2D.conv).  The A operand is not a matrix: an M tile is a 16 x 8
+// patch of OUTPUT pixels, a k-block is (tap, 64 input channels), and its A tile is one TMA box of the image shifted by the tap --
+// out-of-bounds pixels read as zero, which is the padding.  W is [Cout, 9 * Cin] with k = tap * Cin + c.
+struct ConvGeom {
+  int mode;        // 0 plain GEMM | 1: stride 1, pad 1, map [C, W, H, B] | 2: stride 2, pad (0,1,0,1), map [C, 2, W_in/2, 2, H_in/2] of ONE image
+  int H, W;        // output height / width
+  int tiles_x, tiles_y, n_patches;  // 16-wide x 8-high patches per image row / column; B * tiles_y * tiles_x
+  int cin_blocks;  // Cin / 64
+};
+constexpr int kConvPatchW = 16, kConvPatchH = 8;
+
 struct GemmParams {
   int N, K;
   int num_groups;
@@ -59,6 +72,7 @@ struct GemmParams {
   float rms_eps;
   const float* dt_ptr;  // EULER: device scalar float(bf16(sigma_next - sigma))
   int debug_flags;      // bit 0: A loads with L2 evict_last, bit 1: B (weight) loads with L2 evict_first
+  ConvGeom conv;        // conv.mode != 0: g[0].M = B * H * W output pixels, K = 9 * Cin, tmA0 is the image map (see ConvGeom)
   int m_band;           // tile order: 0 = M-fastest over all M tiles (a wave spans every M tile and a few N tiles: each weight tile
                         // is fetched once, A must stay in L2); b > 0 = bands of b M tiles, inside a band M-fastest over all N tiles
                         // (a wave spans b M tiles x all N tiles: for wide-K GEMMs whose A is larger than the L2)
@@ -191,6 +205,19 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int grp,
       tmem_ld_wait();
       linear_out(v, G.bias, n, p.N, x);
       const int no = n_out0 + c * 32;
+      if (mode == EPI_STORE_F32) {
+        if (row_ok) {
+          float* o = reinterpret_cast<float*>(G.out) + (long long)m_local * G.ldo + no;
+          if (n + 32 <= p.N) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(o)[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          } else {
+            for (int i = 0; i < 32 && n + i < p.N; ++i) o[i] = __uint_as_float(v[i]);
+          }
+        }
+        continue;
+      }
       if (mode == EPI_GELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = gelu_tanh(x[i]);
@@ -306,12 +333,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
   pdl_wait();  // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   // ---- tile schedule (identical in every role)
-  const int mt0 = (p.g[0].M + Cfg::kTileM - 1) / Cfg::kTileM;
+  const int mt0 = p.conv.mode ? (p.conv.n_patches + kCtaGroup - 1) / kCtaGroup : (p.g[0].M + Cfg::kTileM - 1) / Cfg::kTileM;
   const int mt1 = (p.num_groups > 1) ? (p.g[1].M + Cfg::kTileM - 1) / Cfg::kTileM : 0;
   const int MT = mt0 + mt1;
   const int NT = (p.N + kBN - 1) / kBN;
   const int num_tiles = MT * NT;
-  const int KBm = p.K / kGemmBlockK;                 // k-blocks whose A operand is the main descriptor
+  const int KBm = (p.K + kGemmBlockK - 1) / kGemmBlockK;  // k-blocks whose A operand is the main descriptor (a ragged last one is zero-filled by TMA)
   const int KB = KBm + p.k_ext / kGemmBlockK;        // + the extension block (0 or 1)
   const int first_tile = blockIdx.x / kCtaGroup;
   const int tile_step = gridDim.x / kCtaGroup;
@@ -333,6 +360,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       const CUtensorMap* tAe = grp ? &tmE1 : &tmE0;
       const CUtensorMap* tBm = grp ? &tmB1 : &tmB0;
       const CUtensorMap* tBe = grp ? &tmF1 : &tmF0;
+      int cimg = 0, cy0 = 0, cx0 = 0;  // convolution: this CTA's patch of output pixels
+      if (p.conv.mode) {
+        const int patch = mi * kCtaGroup + int(cta_rank);
+        const int per = p.conv.tiles_x * p.conv.tiles_y;
+        cimg = patch / per;
+        const int r = patch - cimg * per;
+        cy0 = (r / p.conv.tiles_x) * kConvPatchH;
+        cx0 = (r % p.conv.tiles_x) * kConvPatchW;
+        if (patch >= p.conv.n_patches) { cimg = 0; cy0 = p.conv.H + 64; }  // phantom half of the last pair: every pixel out of bounds
+      }
       for (int kb = 0; kb < KB; ++kb) {
         if constexpr (kCtaGroup == 2) mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
         else mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -342,7 +379,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         const CUtensorMap* tA = kb < KBm ? tAm : tAe;
         const CUtensorMap* tB = kb < KBm ? tBm : tBe;
         const int k_col = (kb < KBm ? kb : kb - KBm) * kGemmBlockK;
-        if constexpr (kCtaGroup == 2) {
+        if (p.conv.mode) {
+          const int tap = kb / p.conv.cin_blocks, cb = kb - tap * p.conv.cin_blocks;
+          const int ky = tap / 3, kx = tap - 3 * ky;
+          if (p.conv.mode == 1)
+            tma_load_4d<kCtaGroup == 2>(tA, &full_bar[stage], sa, cb * kGemmBlockK, cx0 + kx - 1, cy0 + ky - 1, cimg, hint_a);
+          else  // input pixel (2y + ky, 2x + kx) = (row parity ky & 1 of row pair y + (ky >> 1), same in x)
+            tma_load_5d<kCtaGroup == 2>(tA, &full_bar[stage], sa, cb * kGemmBlockK, kx & 1, cx0 + (kx >> 1), ky & 1, cy0 + (ky >> 1), hint_a);
+          if constexpr (kCtaGroup == 2) tma_load_2d_2sm(tB, &full_bar[stage], sb, k_col, n0, hint_b);
+          else tma_load_2d(tB, &full_bar[stage], sb, k_col, n0, hint_b);
+        } else if constexpr (kCtaGroup == 2) {
           tma_load_2d_2sm(tA, &full_bar[stage], sa, k_col, m0, hint_a);
           tma_load_2d_2sm(tB, &full_bar[stage], sb, k_col, n0, hint_b);
         } else {
@@ -407,7 +453,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
       int mi, ni;
       gemm_tile_coords(t, MT, NT, p.m_band, mi, ni);
       const int grp = (mi < mt0) ? 0 : 1;
-      const int m_local = (grp ? mi - mt0 : mi) * Cfg::kTileM + int(cta_rank) * 128 + quad * 32 + lane;
+      int m_local = (grp ? mi - mt0 : mi) * Cfg::kTileM + int(cta_rank) * 128 + quad * 32 + lane;
+      if (p.conv.mode) {  // row r of the patch is output pixel (y0 + r / 16, x0 + r % 16) of image `img`
+        const int patch = mi * kCtaGroup + int(cta_rank), r = quad * 32 + lane;
+        const int per = p.conv.tiles_x * p.conv.tiles_y;
+        const int img = patch / per, pr = patch - img * per;
+        const int y = (pr / p.conv.tiles_x) * kConvPatchH + r / kConvPatchW, x = (pr % p.conv.tiles_x) * kConvPatchW + r % kConvPatchW;
+        m_local = (patch < p.conv.n_patches && y < p.conv.H && x < p.conv.W) ? (img * p.conv.H + y) * p.conv.W + x : p.g[0].M;
+      }
       const int n_tile0 = ni * kBN;
 
       if constexpr (kCtaGroup == 2) mbar_wait_cluster(&tmem_full_bar[acc], acc_phase);

@@ -174,6 +174,41 @@ __device__ __forceinline__ void tma_load_3d_2sm(const void* tmap, uint64_t* bar,
       : "memory");
 }
 
+// 4-D / 5-D tile loads (implicit-GEMM convolution: a [C, W, H, B] or [C, 2, W/2, 2, H/2] view of an NHWC image; coordinates may
+// be negative or past the end -- out-of-bounds elements are zero-filled, which is the convolution's padding).  k2sm: cta_group::2 form.
+template <bool k2sm>
+__device__ __forceinline__ void tma_load_4d(const void* tmap, uint64_t* bar, void* dst, int32_t c0, int32_t c1, int32_t c2, int32_t c3,
+                                            uint64_t hint) {
+  if constexpr (k2sm) {
+    uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
+        : "memory");
+  }
+}
+template <bool k2sm>
+__device__ __forceinline__ void tma_load_5d(const void* tmap, uint64_t* bar, void* dst, int32_t c0, int32_t c1, int32_t c2, int32_t c3,
+                                            int32_t c4, uint64_t hint) {
+  if constexpr (k2sm) {
+    uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(mbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(hint)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6, %7}], [%2], %8;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(hint)
+        : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ tcgen05
 template <int kCtaGroup>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {

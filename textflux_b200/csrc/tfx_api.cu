@@ -22,6 +22,7 @@
 #include "gemm.cuh"
 #include "pointwise.cuh"
 #include "probe.cuh"
+#include "vae.cuh"
 
 using namespace tfx;
 typedef __nv_bfloat16 bf16;
@@ -203,6 +204,8 @@ void configure_kernels(std::string* err_) {
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 224>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 224>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 192>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 192>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 128>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1, 64>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_tcgen05_kernel<2, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<2, 64>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(gemm_mc_tcgen05_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmMcCfg<256, 1>::kSmemBytes));
@@ -259,7 +262,8 @@ void launch_gemm_inst(const LaunchCtx& c, long long tiles, const CUtensorMap& a0
 void launch_gemm(const LaunchCtx& c, int cta_group, int block_n, const CUtensorMap& a0, const CUtensorMap& a1,
                  const CUtensorMap& b0, const CUtensorMap& b1, const GemmParams& p, const GemmExt* ext = nullptr) {
   std::string* err_ = c.err_;
-  REQUIRE(p.K % kGemmBlockK == 0 && p.K > 0, TFX_ERR_INVALID, "GEMM K=%d must be a positive multiple of %d", p.K, kGemmBlockK);
+  // K need not fill its last 64-wide k-block: TMA zero-fills both operands past K (the descriptors check the 16-byte row stride)
+  REQUIRE(p.K > 0, TFX_ERR_INVALID, "GEMM K=%d must be positive", p.K);
   REQUIRE(p.k_ext == 0 || (p.k_ext == kGemmBlockK && ext), TFX_ERR_INVALID, "k_ext %d needs extension descriptors", p.k_ext);
   REQUIRE(p.n_split == p.N || p.n_split % block_n == 0, TFX_ERR_INVALID, "n_split %d not tile aligned", p.n_split);
   const bool qkv = p.mode0 == EPI_QKV || (p.n_split < p.N && p.mode1 == EPI_QKV);
@@ -268,6 +272,7 @@ void launch_gemm(const LaunchCtx& c, int cta_group, int block_n, const CUtensorM
   const int tile_m = 128 * cta_group;
   long long tiles = 0;
   for (int g = 0; g < p.num_groups; ++g) tiles += (p.g[g].M + tile_m - 1) / tile_m;
+  if (p.conv.mode) tiles = (p.conv.n_patches + cta_group - 1) / cta_group;  // convolution: an M tile is one 16 x 8 pixel patch per CTA
   tiles *= (p.N + block_n - 1) / block_n;
   if (tiles == 0) return;
   const int key = cta_group * 1000 + block_n;
@@ -278,6 +283,8 @@ void launch_gemm(const LaunchCtx& c, int cta_group, int block_n, const CUtensorM
     case 2224: launch_gemm_inst<2, 224>(c, tiles, a0, a1, b0, b1, ext, p); break;
     case 1192: launch_gemm_inst<1, 192>(c, tiles, a0, a1, b0, b1, ext, p); break;
     case 2192: launch_gemm_inst<2, 192>(c, tiles, a0, a1, b0, b1, ext, p); break;
+    case 1128: launch_gemm_inst<1, 128>(c, tiles, a0, a1, b0, b1, ext, p); break;
+    case 2128: launch_gemm_inst<2, 128>(c, tiles, a0, a1, b0, b1, ext, p); break;
     case 1064: launch_gemm_inst<1, 64>(c, tiles, a0, a1, b0, b1, ext, p); break;
     case 2064: launch_gemm_inst<2, 64>(c, tiles, a0, a1, b0, b1, ext, p); break;
     default: REQUIRE(false, TFX_ERR_INVALID, "no GEMM instance for cta_group %d block_n %d", cta_group, block_n);
@@ -1868,3 +1875,5 @@ int tfx_op_umma_probe(const void* A, const void* Bm, void* D_f32, int32_t n_dim,
 }
 
 }  // extern "C"
+
+#include "vae_host.inl"
