@@ -5,13 +5,15 @@ Public surface (mirrors what the reference pipeline touches)
     B200FlowMatchEulerScheduler   drop-in for FlowMatchEulerDiscreteScheduler on `pipe.scheduler`
     B200StochasticRFOvershotScheduler   drop-in for StochasticRFOvershotDiscreteScheduler (TextFlux's "overshoot" sampler)
     attach(pipe)                  swap both into a loaded FluxFillPipeline
+    B200AutoencoderKL             drop-in for AutoencoderKL on `pipe.vae` (encode / decode)
     conditioning                  pack/unpack/mask-pack kernels mirroring FluxFillPipeline._pack_latents & co
     loader                        safetensors / LoRA files straight into the packed weight layout
 """
 from .engine import (B200FlowMatchEulerScheduler, B200FluxTransformer, B200StochasticRFOvershotScheduler,  # noqa: F401
                      FrozenConfig, attach, calculate_shift)
 from . import conditioning  # noqa: F401
+from .vae import B200AutoencoderKL  # noqa: F401
 from .packer import fold_lora, lora_modules, pack_weights, packed_layout, reference_names, repack_modules, synthetic_getter  # noqa: F401
 
-__all__ = ["B200FluxTransformer", "B200FlowMatchEulerScheduler", "B200StochasticRFOvershotScheduler", "attach", "calculate_shift", "fold_lora",
+__all__ = ["B200FluxTransformer", "B200AutoencoderKL", "B200FlowMatchEulerScheduler", "B200StochasticRFOvershotScheduler", "attach", "calculate_shift", "fold_lora",
            "pack_weights", "packed_layout", "repack_modules", "lora_modules", "reference_names", "synthetic_getter", "FrozenConfig"]

@@ -676,9 +676,11 @@ def _active_adapters(layer) -> List[str]:
     return [a for a in act if a in layer.lora_A]
 
 
-def attach(pipe, **engine_kw):
+def attach(pipe, vae="auto", **engine_kw):
     """Swap the engine into a loaded reference FluxFillPipeline in place (zero edits to reference files):
-    `pipe.transformer` -> B200FluxTransformer built from the loaded weights, `pipe.scheduler` -> fused scheduler."""
+    `pipe.transformer` -> B200FluxTransformer built from the loaded weights, `pipe.scheduler` -> fused scheduler, and `pipe.vae` ->
+    B200AutoencoderKL (`vae=True`: required; "auto": when the VAE's config is one the engine implements, else the reference VAE stays;
+    False: never)."""
     eng = B200FluxTransformer.from_reference(pipe.transformer, device=pipe.transformer.device, **engine_kw)
     if type(pipe.scheduler).__name__ == "StochasticRFOvershotDiscreteScheduler":
         sch = B200StochasticRFOvershotScheduler.from_config(pipe.scheduler.config)
@@ -686,6 +688,13 @@ def attach(pipe, **engine_kw):
         sch.set_overshot_func(getattr(pipe.scheduler, "overshot_func", lambda t, dt: t + dt))
     else:
         sch = B200FlowMatchEulerScheduler.from_config(pipe.scheduler.config)
+    if vae and getattr(pipe, "vae", None) is not None and type(pipe.vae).__name__ == "AutoencoderKL":
+        from .vae import B200AutoencoderKL
+        try:
+            pipe.vae = B200AutoencoderKL.from_reference(pipe.vae, device=eng.device)
+        except ValueError:
+            if vae is True:
+                raise
     pipe.transformer = eng
     pipe.scheduler = sch
     return pipe

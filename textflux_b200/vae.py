@@ -60,8 +60,9 @@ class B200DiagonalGaussian:
         L = L2 // 2
         noise = _randn_tensor((B, L, h, w), generator, self.parameters.device, self.parameters.dtype).contiguous()
         out = torch.empty_like(noise)
+        params = self.parameters.contiguous()  # [B, 2L, h, w] row-major for the kernel (a caller-built tensor may be channels-last)
         with torch.cuda.device(self.parameters.device):
-            _lib.check(self._lib.tfx_op_gaussian_sample(self.parameters.data_ptr(), noise.data_ptr(), out.data_ptr(), B, L, h * w,
+            _lib.check(self._lib.tfx_op_gaussian_sample(params.data_ptr(), noise.data_ptr(), out.data_ptr(), B, L, h * w,
                                                         torch.cuda.current_stream().cuda_stream))
         return out
 
