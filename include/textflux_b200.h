@@ -219,6 +219,46 @@ int tfx_vae_decode(tfx_vae_handle h, const void* latents, int32_t B, int32_t h_l
  * moments [B, 2 * latent_channels, hw] bf16 (mean ; logvar), noise / out [B, latent_channels, hw] bf16 */
 int tfx_op_gaussian_sample(const void* moments, const void* noise, void* out, int32_t B, int32_t latent_channels, int64_t hw, void* stream);
 
+/* ---- prompt encoders: text_encoder_2 = T5EncoderModel (T5-XXL v1.1), text_encoder = CLIPTextModel
+ * (CLIP-L), called at pipeline_flux_fill.py:1411-1503 (_get_t5_prompt_embeds :1438, _get_clip_prompt_embeds :1483).  Both live in the
+ * third-party `transformers` package (reference pin 4.43.3, requirements.txt:4): models/t5/modeling_t5.py, models/clip/modeling_clip.py.
+ * Tokenisation stays with the caller (transformers' tokenizers on the host); these entry points start at input_ids. ------------------ */
+typedef struct tfx_textenc* tfx_textenc_handle;
+enum { TFX_TEXTENC_T5 = 0, TFX_TEXTENC_CLIP = 1 };
+
+/* T5Config / CLIPTextConfig fields the encoders read */
+typedef struct {
+  int32_t kind;              /* TFX_TEXTENC_T5: encoder-only T5 v1.1 (gated-gelu, RMS norm, relative position bias, no biases);
+                                TFX_TEXTENC_CLIP: CLIP text transformer (pre-LN, causal mask, quick_gelu) */
+  int32_t vocab_size;        /* 32128 | 49408 */
+  int32_t d_model;           /* 4096 | 768 (hidden_size) */
+  int32_t d_kv;              /* 64 (head dimension; CLIP: hidden_size / num_attention_heads) */
+  int32_t num_heads;         /* 64 | 12 */
+  int32_t num_layers;        /* 24 | 12 */
+  int32_t d_ff;              /* 10240 | 3072 (intermediate_size) */
+  int32_t max_positions;     /* CLIP: max_position_embeddings (77) */
+  int32_t rel_buckets;       /* T5: relative_attention_num_buckets (32) */
+  int32_t rel_max_distance;  /* T5: relative_attention_max_distance (128) */
+  float eps;                 /* layer_norm_epsilon 1e-6 | layer_norm_eps 1e-5 */
+} tfx_textenc_config;
+
+int tfx_textenc_create(const tfx_textenc_config* cfg, int32_t device, tfx_textenc_handle* out);
+void tfx_textenc_destroy(tfx_textenc_handle h);
+const char* tfx_textenc_last_error(tfx_textenc_handle h);
+int tfx_textenc_get_counter(tfx_textenc_handle h, const char* key, int64_t* value);
+/* bf16 device tensors under packed names: "embed" [vocab, D]; per layer i "l<i>.ln1.w", "l<i>.qkv.w" [3 H 64, D]
+ * (q ; k ; v rows), "l<i>.o.w" [D, H 64], "l<i>.ln2.w"; T5: "rel_bias" [rel_buckets, H], "l<i>.wi0.w", "l<i>.wi1.w" [d_ff, D],
+ * "l<i>.wo.w" [D, d_ff], "final_ln.w"; CLIP: "pos" [max_positions, D], ".b" next to every ".w", "l<i>.fc1.w" [d_ff, D], "l<i>.fc2.w" */
+int tfx_textenc_set_weight(tfx_textenc_handle h, const char* name, const void* dev_ptr, int64_t rows, int64_t cols);
+/* replaces T5EncoderModel.forward(input_ids)[0] / CLIPTextModel.forward(input_ids) -> (last_hidden_state, pooler_output):
+ *   input_ids [B, T] int32 (device); last_hidden_state [B, T, D] bf16
+ *   rel_bucket_lut (T5) [2T - 1] int32: bucket of relative position d = key - query at index d + T - 1 (T5Attention._relative_position_bucket,
+ *     evaluated by the caller exactly as the reference evaluates it)
+ *   pooled_index (CLIP) [B] int32 = position of each sample's EOS token (argmax rule of CLIPTextTransformer.forward), pooled_out [B, D]
+ *     bf16 = last_hidden_state[b, pooled_index[b]]; both NULL to skip */
+int tfx_textenc_encode(tfx_textenc_handle h, const int32_t* input_ids, int32_t B, int32_t T, const int32_t* rel_bucket_lut,
+                       void* last_hidden_state, const int32_t* pooled_index, void* pooled_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,3 +168,36 @@ def test_vae_oracle_matches_reference_golden(name):
         assert torch.equal(vo.decode(sd, cfg, d["z"].to(dtype)), d[f"decoded_{tag}"])
         noise = torch.randn(d[f"sample_{tag}"].shape, generator=torch.Generator().manual_seed(5), dtype=dtype)
         assert torch.equal(vo.gaussian_sample(m, noise), d[f"sample_{tag}"])
+
+
+# ---------------------------------------------------------------------------------------------- prompt-encoder oracle
+def test_textenc_t5_oracle_matches_transformers_golden():
+    from oracle import textenc_oracle as to
+    d = torch.load(os.path.join(GOLDEN, "textenc_t5.pt"))
+    cfg = to.T5Cfg(**d["config"])
+    sd32 = to.init_state_dict(to.t5_spec(cfg), d["seed"])
+    for dtype, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        assert torch.equal(to.t5_encode({k: v.to(dtype) for k, v in sd32.items()}, cfg, d["input_ids"]), d[f"last_hidden_{tag}"])
+
+
+def test_textenc_clip_oracle_matches_transformers_golden():
+    from oracle import textenc_oracle as to
+    d = torch.load(os.path.join(GOLDEN, "textenc_clip.pt"))
+    cfg = to.ClipCfg(**d["config"])
+    sd32 = to.init_state_dict(to.clip_spec(cfg), d["seed"])
+    for dtype, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        lh, po = to.clip_encode({k: v.to(dtype) for k, v in sd32.items()}, cfg, d["input_ids"])
+        assert torch.equal(lh, d[f"last_hidden_{tag}"]) and torch.equal(po, d[f"pooled_{tag}"])
+
+
+def test_t5_bucket_table_of_the_engine_equals_the_reference_bucket_function():
+    """The host-side table the engine hands to tfx_textenc_encode (textflux_b200.text_encoders.t5_bucket_lut) against
+    T5Attention._relative_position_bucket evaluated over the whole [T, T] grid -- index math, bit-exact."""
+    from oracle import textenc_oracle as to
+    from textflux_b200.text_encoders import t5_bucket_lut
+    for T in (1, 7, 48, 77, 512):
+        lut = t5_bucket_lut(T, 32, 128)
+        ctx = torch.arange(T)[:, None]
+        mem = torch.arange(T)[None, :]
+        ref = to.t5_relative_position_bucket(mem - ctx, 32, 128)
+        assert torch.equal(lut[(mem - ctx) + T - 1].long(), ref)

@@ -14,6 +14,12 @@ class TfxVaeConfig(C.Structure):
                 ("mid_block_add_attention", C.c_int32)]
 
 
+class TfxTextEncConfig(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("vocab_size", C.c_int32), ("d_model", C.c_int32), ("d_kv", C.c_int32), ("num_heads", C.c_int32),
+                ("num_layers", C.c_int32), ("d_ff", C.c_int32), ("max_positions", C.c_int32), ("rel_buckets", C.c_int32),
+                ("rel_max_distance", C.c_int32), ("eps", C.c_float)]
+
+
 class TfxConfig(C.Structure):
     _fields_ = [("in_channels", C.c_int32), ("out_channels", C.c_int32), ("num_layers", C.c_int32),
                 ("num_single_layers", C.c_int32), ("attention_head_dim", C.c_int32),
@@ -63,6 +69,12 @@ SIGNATURES = {
     "tfx_vae_encode": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "tfx_vae_decode": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "tfx_op_gaussian_sample": (C.c_int, [_P, _P, _P, _I32, _I32, _I64, _P]),
+    "tfx_textenc_create": (C.c_int, [C.POINTER(TfxTextEncConfig), _I32, C.POINTER(_P)]),
+    "tfx_textenc_destroy": (None, [_P]),
+    "tfx_textenc_last_error": (C.c_char_p, [_P]),
+    "tfx_textenc_get_counter": (C.c_int, [_P, C.c_char_p, C.POINTER(_I64)]),
+    "tfx_textenc_set_weight": (C.c_int, [_P, C.c_char_p, _P, _I64, _I64]),
+    "tfx_textenc_encode": (C.c_int, [_P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
     "tfx_op_umma_probe": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _U32, _U32, _U32, _P]),
 }
 
@@ -93,9 +105,10 @@ class TfxError(RuntimeError):
         self.code = code
 
 
-def check(code: int, handle=None, vae: bool = False):
+def check(code: int, handle=None, vae: bool = False, textenc: bool = False):
     if code != 0:
-        msg = load().tfx_vae_last_error(handle) if vae else load().tfx_last_error(handle)
+        lib = load()
+        msg = lib.tfx_vae_last_error(handle) if vae else lib.tfx_textenc_last_error(handle) if textenc else lib.tfx_last_error(handle)
         text = msg.decode() if msg else "unknown error"
         if code == 1:
             raise ValueError(f"textflux_b200: {text}")  # the reference raises ValueError on bad inputs

@@ -11,7 +11,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libtextflux_b200.so")
 SOURCES = ["tfx_api.cu"]
 HEADERS = ["ptx.cuh", "gemm.cuh", "attention_common.cuh", "attention3.cuh", "attention4.cuh", "attention5.cuh", "conditioning.cuh",
-           "pointwise.cuh", "probe.cuh", "vae.cuh", "vae_host.inl"]
+           "pointwise.cuh", "probe.cuh", "vae.cuh", "vae_host.inl", "textenc.cuh", "textenc_host.inl"]
 
 
 def _nvcc() -> str:

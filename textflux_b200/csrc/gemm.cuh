@@ -23,6 +23,8 @@ namespace tfx {
 
 enum EpiMode : int {
   EPI_STORE = 0,     // out = bf16(acc + bias)
+  EPI_MUL = 6,         // out = bf16(res * bf16(acc + bias)): the gated half of T5's DenseGatedActDense (hidden_gelu * hidden_linear)
+  EPI_QUICK_GELU = 7,  // out = bf16(x * sigmoid(1.702 x)), x = bf16(acc + bias): CLIP's MLP activation
   EPI_STORE_F32 = 5,  // out (float*, ldo in floats) = acc, no bias: attention scores of the VAE mid block, kept in fp32 for the softmax
   EPI_GELU = 1,      // out = bf16(gelu_tanh(bf16(acc + bias)))
   EPI_GATE_RES = 2,  // out = bf16(res + bf16(gate * bf16(acc + bias)))
@@ -221,6 +223,20 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int grp,
       if (mode == EPI_GELU) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) x[i] = gelu_tanh(x[i]);
+      } else if (mode == EPI_QUICK_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = x[i] / (1.0f + __expf(-1.702f * x[i]));
+      } else if (mode == EPI_MUL) {
+        if (row_ok) {
+          if (n + 32 <= p.N) {
+            float r[32];
+            load_bf16x32<false>(G.res + (long long)m_local * G.ldr + no, r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) x[i] *= r[i];
+          } else {
+            for (int i = 0; i < 32 && n + i < p.N; ++i) x[i] *= __bfloat162float(G.res[(long long)m_local * G.ldr + no + i]);
+          }
+        }
       } else if (mode == EPI_GATE_RES) {
         if (row_ok) {
           float g[32], r[32];

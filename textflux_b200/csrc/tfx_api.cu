@@ -22,6 +22,7 @@
 #include "gemm.cuh"
 #include "pointwise.cuh"
 #include "probe.cuh"
+#include "textenc.cuh"
 #include "vae.cuh"
 
 using namespace tfx;
@@ -1877,3 +1878,4 @@ int tfx_op_umma_probe(const void* A, const void* Bm, void* D_f32, int32_t n_dim,
 }  // extern "C"
 
 #include "vae_host.inl"
+#include "textenc_host.inl"

@@ -676,11 +676,11 @@ def _active_adapters(layer) -> List[str]:
     return [a for a in act if a in layer.lora_A]
 
 
-def attach(pipe, vae="auto", **engine_kw):
+def attach(pipe, vae="auto", text_encoders="auto", **engine_kw):
     """Swap the engine into a loaded reference FluxFillPipeline in place (zero edits to reference files):
-    `pipe.transformer` -> B200FluxTransformer built from the loaded weights, `pipe.scheduler` -> fused scheduler, and `pipe.vae` ->
-    B200AutoencoderKL (`vae=True`: required; "auto": when the VAE's config is one the engine implements, else the reference VAE stays;
-    False: never)."""
+    `pipe.transformer` -> B200FluxTransformer built from the loaded weights, `pipe.scheduler` -> fused scheduler, `pipe.vae` ->
+    B200AutoencoderKL and `pipe.text_encoder` / `pipe.text_encoder_2` -> B200CLIPTextEncoder / B200T5Encoder (`True`: required;
+    "auto": when the module's config is one the engine implements, else the reference module stays; False: never)."""
     eng = B200FluxTransformer.from_reference(pipe.transformer, device=pipe.transformer.device, **engine_kw)
     if type(pipe.scheduler).__name__ == "StochasticRFOvershotDiscreteScheduler":
         sch = B200StochasticRFOvershotScheduler.from_config(pipe.scheduler.config)
@@ -695,6 +695,17 @@ def attach(pipe, vae="auto", **engine_kw):
         except ValueError:
             if vae is True:
                 raise
+    if text_encoders:
+        from .text_encoders import B200CLIPTextEncoder, B200T5Encoder
+        for attr, ref_cls, cls in (("text_encoder", "CLIPTextModel", B200CLIPTextEncoder), ("text_encoder_2", "T5EncoderModel", B200T5Encoder)):
+            mod = getattr(pipe, attr, None)
+            if mod is None or type(mod).__name__ != ref_cls:
+                continue
+            try:
+                setattr(pipe, attr, cls.from_reference(mod, device=eng.device))
+            except ValueError:
+                if text_encoders is True:
+                    raise
     pipe.transformer = eng
     pipe.scheduler = sch
     return pipe
