@@ -500,6 +500,7 @@ def run_ours(args, name):
         if world > 1:
             dist.destroy_process_group()
         return
+    once = None if args.no_image_stages else once_per_image(inp, dev, ms / args.steps)
 
     total_steps = args.steps * B * world
     value = total_steps / (ms / 1e3)
@@ -538,13 +539,65 @@ def run_ours(args, name):
             "clocks": clocks, "gpu_launches": launches, "finite": finite,
             "e2e": {"value": total_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "roofline": roof, "dropin": dropin, "configs": configs, "parity": parity, "gpu_eager_baseline": gpu_eager,
-            "cpu_baseline": cpu}
+            "once_per_image": once, "cpu_baseline": cpu}
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
+
+
+def once_per_image(inp, dev, ms_per_step):
+    """The stages FluxFillPipeline runs once per image around the loop, on the engine, NOT part of `value`:
+    vae.encode of the masked canvas (:1528), vae.decode (:2128), T5-XXL and CLIP-L prompt encoding (:1438, :1483).  Synthetic weights of
+    the real shapes, CUDA events, median of 5."""
+    from textflux_b200 import B200AutoencoderKL, B200CLIPTextEncoder, B200T5Encoder
+    from textflux_b200.text_encoders import CLIP_L_CONFIG, T5_XXL_CONFIG, clip_reference_names, t5_reference_names
+    from textflux_b200.vae import FLUX_VAE_CONFIG, synthetic_state, vae_reference_names
+
+    def med(fn, iters=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize(dev)
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[len(ts) // 2]
+
+    out = {}
+    try:
+        H, W = inp.h2 * 16, inp.w2 * 16
+        vae = B200AutoencoderKL.from_state_dict(FLUX_VAE_CONFIG, synthetic_state(vae_reference_names(FLUX_VAE_CONFIG), 31, dev), device=dev)
+        g = torch.Generator(device=dev).manual_seed(5)
+        image = (torch.rand(1, 3, H, W, generator=g, device=dev) * 2 - 1).to(torch.bfloat16)
+        z = torch.randn(1, 16, H // 8, W // 8, generator=g, device=dev).to(torch.bfloat16)
+        out["canvas"] = f"{H}x{W}"
+        out["vae_encode_ms"], out["vae_decode_ms"] = med(lambda: vae.encode(image)), med(lambda: vae.decode(z))
+        out["vae_finite"] = bool(torch.isfinite(vae.decode(z, return_dict=False)[0].float()).all())
+        out["vae_launches"] = vae.counter("launches")
+        del vae
+        t5 = B200T5Encoder(T5_XXL_CONFIG, synthetic_state(t5_reference_names(T5_XXL_CONFIG), 7, dev).__getitem__, device=dev)
+        ids = torch.randint(2, 32128, (1, 512), device=dev)
+        ids[:, 60:] = 0
+        out["t5_xxl_ms"] = med(lambda: t5(ids))
+        out["t5_launches"] = t5.counter("launches")
+        del t5
+        clip = B200CLIPTextEncoder(CLIP_L_CONFIG, synthetic_state(clip_reference_names(CLIP_L_CONFIG), 8, dev).__getitem__, device=dev, cache=False)
+        cids = torch.randint(3, 49406, (1, 77), device=dev)
+        cids[:, 30:] = 49407
+        out["clip_l_ms"] = med(lambda: clip(cids))
+        del clip
+        torch.cuda.empty_cache()
+        stages = out["vae_encode_ms"] + out["vae_decode_ms"] + out["t5_xxl_ms"] + out["clip_l_ms"]
+        out["stages_ms"] = stages
+        out["share_of_a_30_step_image"] = stages / (stages + 30 * ms_per_step)
+    except Exception as e:  # never let the side stages take the bench line down
+        out["error"] = repr(e)[:300]
+    return out
 
 
 class EagerReference:
@@ -663,6 +716,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the CUDA-eager reference baseline and the parity legs")
     ap.add_argument("--no-fp32-floor", action="store_true")
+    ap.add_argument("--no-image-stages", action="store_true", help="skip the once-per-image stages (VAE, prompt encoders)")
     ap.add_argument("--no-configs", action="store_true", help="skip the secondary configurations")
     ap.add_argument("--no-schedule", action="store_true", help="recompute the adaLN modulation every step inside the fused step")
     args = ap.parse_args()

@@ -124,6 +124,48 @@ def test_unmodified_pipeline_with_engine_and_vae_attached():
         textflux_b200.attach(_tiny_pipeline(False), vae=True)
 
 
+def test_attach_swaps_the_prompt_encoders():
+    """attach(pipe, text_encoders=True): transformers' CLIPTextModel / T5EncoderModel on pipe.text_encoder / text_encoder_2 become the
+    engine's mirrors and answer the two calls of pipeline_flux_fill.py:1438 / :1483 like the stock modules (the tokenizers need vocabulary
+    files that are not in the image, so the pipeline object here is the attribute bag attach() works on, not FluxFillPipeline)."""
+    from types import SimpleNamespace
+    from transformers import CLIPTextConfig, CLIPTextModel, T5Config, T5EncoderModel
+    import textflux_b200
+    from textflux_b200 import B200CLIPTextEncoder, B200FluxTransformer, B200T5Encoder
+    torch.manual_seed(0)
+    t5 = T5EncoderModel(T5Config(vocab_size=300, d_model=256, d_kv=64, d_ff=512, num_layers=2, num_heads=4, feed_forward_proj="gated-gelu",
+                                 dropout_rate=0.0, tie_word_embeddings=False, is_encoder_decoder=False, use_cache=False)).to("cuda", torch.bfloat16).eval()
+    ccfg = CLIPTextConfig(vocab_size=500, hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                          max_position_embeddings=77, hidden_act="quick_gelu", eos_token_id=2, bos_token_id=0, pad_token_id=1)
+    ccfg._attn_implementation = "eager"
+    clip = CLIPTextModel(ccfg).to("cuda", torch.bfloat16).eval()
+    cfg = fo.TINY
+    ra_ok = ra.available()
+    if ra_ok:
+        ra.import_reference()
+        from diffusers import FlowMatchEulerDiscreteScheduler, FluxTransformer2DModel
+        tr = FluxTransformer2DModel(**cfg.to_dict())
+        tr.load_state_dict(fo.init_state_dict(cfg, seed=1234, dtype=torch.float32))
+        tr = tr.to("cuda", torch.bfloat16)
+        sch = FlowMatchEulerDiscreteScheduler(use_dynamic_shifting=True, base_shift=0.5, max_shift=1.15)
+    else:
+        pytest.skip("reference not installed under baseline/_ref")
+    pipe = SimpleNamespace(transformer=tr, scheduler=sch, vae=None, text_encoder=clip, text_encoder_2=t5)
+    ids5 = torch.randint(2, 300, (1, 64), device="cuda")
+    idsc = torch.randint(3, 498, (1, 77), device="cuda")
+    idsc[:, 40:] = 499
+    with torch.no_grad():
+        ref5 = t5(ids5, output_hidden_states=False)[0]
+        refc = clip(idsc, output_hidden_states=False).pooler_output
+    textflux_b200.attach(pipe, text_encoders=True)
+    assert isinstance(pipe.text_encoder, B200CLIPTextEncoder) and isinstance(pipe.text_encoder_2, B200T5Encoder) and isinstance(pipe.transformer, B200FluxTransformer)
+    out5 = pipe.text_encoder_2(ids5, output_hidden_states=False)[0]
+    outc = pipe.text_encoder(idsc, output_hidden_states=False).pooler_output
+    print(f"attach: T5 rel-L2 {_rel(out5, ref5):.3e} cosdist {_cosdist(out5, ref5):.2e} | CLIP pooled rel-L2 {_rel(outc, refc):.3e} cosdist {_cosdist(outc, refc):.2e}")
+    assert out5.shape == ref5.shape and outc.shape == refc.shape and out5.dtype == outc.dtype == torch.bfloat16
+    assert _cosdist(out5, ref5) < 1e-3 and _cosdist(outc, refc) < 1e-3
+
+
 def _engine(cfg, sd, **kw):
     from textflux_b200 import B200FluxTransformer
     return B200FluxTransformer.from_state_dict(cfg.to_dict(), sd, device="cuda:0", **kw)

@@ -266,9 +266,22 @@ def test_linear_strided_a(lib):
     assert _rel(out, A.float() @ W.float().T) < 4e-3
 
 
-def test_linear_rejects_bad_k(lib):
-    A = torch.zeros(128, 72, device="cuda", dtype=torch.bfloat16)
-    W = torch.zeros(64, 72, device="cuda", dtype=torch.bfloat16)
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("K", [72, 8, 200])
+def test_linear_ragged_k(lib, K, cta_group):
+    """K need not fill its last 64-wide k-block: TMA zero-fills both operands past K (the VAE's P v product has K = latent pixels)."""
+    g = torch.Generator(device="cuda").manual_seed(K)
+    A = torch.randn(300, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(320, K, generator=g, device="cuda") * 0.1).to(torch.bfloat16)
+    b = torch.randn(320, generator=g, device="cuda").to(torch.bfloat16)
+    out = _linear(lib, A, W, b, 0, cta_group)
+    assert _rel(out, A.float() @ W.float().T + b.float()) < 4e-3
+
+
+def test_linear_rejects_unaligned_rows(lib):
+    """Rows of either operand must be 16-byte aligned for TMA: K = 68 with a row stride of 68 elements (136 bytes) is refused."""
+    A = torch.zeros(128, 68, device="cuda", dtype=torch.bfloat16)
+    W = torch.zeros(64, 68, device="cuda", dtype=torch.bfloat16)
     b = torch.zeros(64, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(ValueError):
         _linear(lib, A, W, b, 0, 1)

@@ -124,6 +124,41 @@ def t5_bucket_lut(T: int, num_buckets: int, max_distance: int) -> Tensor:
     return (buckets + torch.where(is_small, rp, large)).to(torch.int32)
 
 
+T5_XXL_CONFIG = dict(vocab_size=32128, d_model=4096, d_kv=64, num_heads=64, num_layers=24, d_ff=10240, relative_attention_num_buckets=32,
+                     relative_attention_max_distance=128, layer_norm_epsilon=1e-6, feed_forward_proj="gated-gelu")
+CLIP_L_CONFIG = dict(vocab_size=49408, hidden_size=768, num_attention_heads=12, num_hidden_layers=12, intermediate_size=3072,
+                     max_position_embeddings=77, layer_norm_eps=1e-5, eos_token_id=2, hidden_act="quick_gelu")
+
+
+def t5_reference_names(cfg) -> list:
+    """(name, shape) of the T5EncoderModel.state_dict() tensors the encoder reads."""
+    inner, D, F = cfg["num_heads"] * cfg["d_kv"], cfg["d_model"], cfg["d_ff"]
+    out = [("shared.weight", (cfg["vocab_size"], D)),
+           ("encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", (cfg.get("relative_attention_num_buckets", 32), cfg["num_heads"]))]
+    for i in range(cfg["num_layers"]):
+        a, f = f"encoder.block.{i}.layer.0", f"encoder.block.{i}.layer.1"
+        out += [(f"{a}.SelfAttention.{m}.weight", (inner, D)) for m in ("q", "k", "v")]
+        out += [(f"{a}.SelfAttention.o.weight", (D, inner)), (f"{a}.layer_norm.weight", (D,)), (f"{f}.layer_norm.weight", (D,)),
+                (f"{f}.DenseReluDense.wi_0.weight", (F, D)), (f"{f}.DenseReluDense.wi_1.weight", (F, D)), (f"{f}.DenseReluDense.wo.weight", (D, F))]
+    out.append(("encoder.final_layer_norm.weight", (D,)))
+    return out
+
+
+def clip_reference_names(cfg) -> list:
+    """(name, shape) of the CLIPTextModel.state_dict() tensors the encoder reads."""
+    D, F = cfg["hidden_size"], cfg["intermediate_size"]
+    out = [("text_model.embeddings.token_embedding.weight", (cfg["vocab_size"], D)),
+           ("text_model.embeddings.position_embedding.weight", (cfg["max_position_embeddings"], D))]
+    for i in range(cfg["num_hidden_layers"]):
+        L = f"text_model.encoder.layers.{i}."
+        for m in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            out += [(f"{L}self_attn.{m}.weight", (D, D)), (f"{L}self_attn.{m}.bias", (D,))]
+        out += [(L + "layer_norm1.weight", (D,)), (L + "layer_norm1.bias", (D,)), (L + "layer_norm2.weight", (D,)), (L + "layer_norm2.bias", (D,)),
+                (L + "mlp.fc1.weight", (F, D)), (L + "mlp.fc1.bias", (F,)), (L + "mlp.fc2.weight", (D, F)), (L + "mlp.fc2.bias", (D,))]
+    out += [("text_model.final_layer_norm.weight", (D,)), ("text_model.final_layer_norm.bias", (D,))]
+    return out
+
+
 class B200T5Encoder(_TextEncoderBase):
     """Drop-in for T5EncoderModel (T5 v1.1 encoder: gated-gelu, RMS layer norm, relative position bias on layer 0 shared by all)."""
 

@@ -89,6 +89,81 @@ def pack_vae_weights(get: Callable[[str], Tensor], names, device, dtype=torch.bf
     return P
 
 
+def vae_reference_names(cfg) -> list:
+    """(name, shape) of every tensor AutoencoderKL.state_dict() holds for `cfg` (dict with in_channels, out_channels, latent_channels,
+    block_out_channels, layers_per_block, mid_block_add_attention): what a checkpoint must provide, and the shapes synthetic weights take."""
+    out = []
+
+    def conv(n, o, i, k=3):
+        out.extend([(n + ".weight", (o, i, k, k)), (n + ".bias", (o,))])
+
+    def vec(n, c):
+        out.extend([(n + ".weight", (c,)), (n + ".bias", (c,))])
+
+    def resnet(n, i, o):
+        vec(n + ".norm1", i); conv(n + ".conv1", o, i); vec(n + ".norm2", o); conv(n + ".conv2", o, o)
+        if i != o:
+            conv(n + ".conv_shortcut", o, i, 1)
+
+    def mid(n, c):
+        resnet(n + ".resnets.0", c, c)
+        if cfg.get("mid_block_add_attention", True):
+            vec(n + ".attentions.0.group_norm", c)
+            for m in ("to_q", "to_k", "to_v", "to_out.0"):
+                out.extend([(f"{n}.attentions.0.{m}.weight", (c, c)), (f"{n}.attentions.0.{m}.bias", (c,))])
+        resnet(n + ".resnets.1", c, c)
+
+    ch = list(cfg["block_out_channels"])
+    conv("encoder.conv_in", ch[0], cfg["in_channels"])
+    c = ch[0]
+    for i, co in enumerate(ch):
+        for j in range(cfg["layers_per_block"]):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", c, co)
+            c = co
+        if i + 1 < len(ch):
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", c, c)
+    mid("encoder.mid_block", c)
+    vec("encoder.conv_norm_out", c)
+    conv("encoder.conv_out", 2 * cfg["latent_channels"], c)
+    conv("decoder.conv_in", ch[-1], cfg["latent_channels"])
+    c = ch[-1]
+    mid("decoder.mid_block", c)
+    for i, co in enumerate(reversed(ch)):
+        for j in range(cfg["layers_per_block"] + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}", c, co)
+            c = co
+        if i + 1 < len(ch):
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", c, c)
+    vec("decoder.conv_norm_out", c)
+    conv("decoder.conv_out", cfg["out_channels"], c)
+    return out
+
+
+def synthetic_state(names, seed: int, device, dtype=torch.bfloat16) -> Dict[str, Tensor]:
+    """Random tensors of the given (name, shape) list, one seeded generator each (bench / smoke: no checkpoints offline): matrices and
+    convolutions N(0, 1 / fan_in), 1-D weights of norms 1 + N(0, 0.1^2), other vectors N(0, 0.02^2)."""
+    sd = {}
+    for idx, (name, shape) in enumerate(names):
+        g = torch.Generator(device=device).manual_seed(seed * 100003 + idx)
+        t = torch.randn(shape, generator=g, device=device, dtype=torch.float32)
+        if len(shape) >= 2:
+            fan = 1
+            for d in shape[1:]:
+                fan *= d
+            t = t * (1.0 / fan) ** 0.5 if "embed" not in name and "shared" not in name else t
+        elif name.endswith(".weight") and ("norm" in name or "ln" in name):
+            t = 1.0 + 0.1 * t
+        else:
+            t = 0.02 * t
+        sd[name] = t.to(dtype)
+    return sd
+
+
+FLUX_VAE_CONFIG = dict(in_channels=3, out_channels=3, latent_channels=16, block_out_channels=(128, 256, 512, 512), layers_per_block=2,
+                       norm_num_groups=32, mid_block_add_attention=True, scaling_factor=0.3611, shift_factor=0.1159,
+                       use_quant_conv=False, use_post_quant_conv=False, act_fn="silu")
+
+
 class B200AutoencoderKL(torch.nn.Module):
     """Drop-in for AutoencoderKL (models/autoencoders/autoencoder_kl.py:35-571) restricted to what FLUX's VAE is: DownEncoderBlock2D /
     UpDecoderBlock2D stacks, SiLU, GroupNorm, one-head mid-block attention, no quant / post-quant convolutions, no tiling / slicing."""
