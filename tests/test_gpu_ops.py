@@ -320,6 +320,37 @@ def test_attention(lib, B, H, T, S, dh, q_tiles):
     assert err < 8e-3, err
 
 
+@pytest.mark.parametrize("q_tiles", [26, 27, 29], ids=["s3split", "persist", "stream"])
+@pytest.mark.parametrize("kind", ["jump", "ramp", "first_tile_peak"])
+def test_attention_on_adversarial_scores(lib, q_tiles, kind):
+    """The lazily rescaled running maximum (attn_softmax_tile: the reference only moves when the true maximum ran away by more than
+    2^8) on scores built to stress it: a key deep in the sequence that beats a row's running maximum by ~2^49, a maximum that
+    climbs by ~2^12 every tile (the accumulator is rescaled tile after tile), and a row whose peak sits in the first tile
+    (everything later underflows towards 0).  The same cases pass with the lag-1 variant (-DTFX_ATTN_LAG=1, profiles/r2m_attn_lag.md)."""
+    H, N, dh, T = 3, 1152, 128, 128
+    g = torch.Generator(device="cuda").manual_seed(77)
+    q = torch.randn(1, H, N, dh, generator=g, device="cuda")
+    k = torch.randn(1, H, N, dh, generator=g, device="cuda")
+    v = torch.randn(1, H, N, dh, generator=g, device="cuda")
+    if kind == "jump":      # keys 700.. are strong copies of queries 0..63: q.k = 3 * |q|^2 ~ 384 -> 49 log2 units above anything else
+        k[:, :, 700:764] = 3.0 * q[:, :, 0:64]
+    elif kind == "ramp":    # key tile t points along one direction with growing length; queries have a component along it
+        u = torch.nn.functional.normalize(torch.randn(dh, generator=g, device="cuda"), dim=0)
+        q = q + 6.0 * u
+        for t in range(N // 128):
+            k[:, :, t * 128:(t + 1) * 128] += (2.2 * t) * u
+    else:
+        k[:, :, 5:40] = 2.5 * q[:, :, 200:235]
+    q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
+    out = _attention(lib, q, k, v, T, q_tiles)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float()).transpose(1, 2).reshape(1, N, H * dh)
+    assert torch.isfinite(out.float()).all()
+    err = _rel(out, ref)
+    lib16 = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(1, N, H * dh)
+    print(f"{kind} code {q_tiles}: ours-vs-fp32 {err:.3e}, torch bf16 SDPA-vs-fp32 {_rel(lib16, ref):.3e}")
+    assert err < 8e-3 and err < 1.5 * _rel(lib16, ref) + 1e-4, err
+
+
 def test_attention_stream_is_deterministic_and_self_cleaning(lib):
     """Schedule 4 merges the parts of a cut unit in part order whoever arrives last, and leaves its ticket counters at 0:
     repeated launches (and launches of other shapes in between) give identical bits."""

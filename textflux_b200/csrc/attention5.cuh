@@ -283,7 +283,6 @@ attention5_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     const uint32_t t_s = t_lane + uint32_t(Cfg::kSCol + q * 128);
     const uint32_t t_o = t_lane + uint32_t(Cfg::kOCol + q * 128);
     const float c = p.scale_log2;
-    const float kRescaleThreshold = 8.0f;  // log2 units: keep a stale row max until it is off by more than 2^8
     int g = 0;
     for (int k = 0;; ++k) {
       int n_it, kv_first;
@@ -293,85 +292,20 @@ attention5_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         n_it = it0.kv1 - it0.kv0;
         kv_first = it0.kv0;
       }
-      float m = -INFINITY, l = 0.f;
+      float m = -INFINITY, l = 0.f, pend = -INFINITY;
       for (int jj = 0; jj < n_it; ++jj, ++g) {
         const int valid = p.N - (kv_first + jj) * 128;  // >= 128 on every tile but possibly the last of the sequence
         mbar_wait(&s_full[q], g & 1);
         tc_fence_after();
         if (kTrace && ctr && jj == 0 && warp == 4 && lane == 0 && k < 8) { ctr[k * 8 + 0] = (long long)globaltimer_ns(); ctr[k * 8 + 7] = n_it; }
-        uint32_t sr[4][32];
-        tmem_ld32(t_s + 0, sr[0]);
-        tmem_ld32(t_s + 32, sr[1]);
-        tmem_ld32(t_s + 64, sr[2]);
-        tmem_ld32(t_s + 96, sr[3]);
-        tmem_ld_wait();
-        if (valid < 128) {  // ragged last tile: keys past N score -inf -> probability 0
-#pragma unroll
-          for (int cch = 0; cch < 4; ++cch)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (cch * 32 + i >= valid) sr[cch][i] = 0xff800000u;
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
-          mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
-          mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        const bool need = (mx - m) * c > kRescaleThreshold;  // true on the first tile (m = -inf)
-        const float m_new = need ? mx : m;
-        const float alpha = need ? ex2((m - m_new) * c) : 1.0f;
-        const float mc = m_new * c;
-        if (jj > 0 && __any_sync(0xffffffffu, need)) {
-          // O_q holds this item's PV(0..jj-1): retired, because QK(jj) was committed behind PV(jj-1) and s_full has flipped
-#pragma unroll 1
-          for (int cch = 0; cch < kHeadDim / 32; ++cch) {
-            uint32_t v[32];
-            tmem_ld32(t_o + cch * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            tmem_st32(t_o + cch * 32, v);
-          }
-          tmem_st_wait();
-        }
-        const f32x2 c2 = pack2(c, c), nmc2 = pack2(-mc, -mc);
-        f32x2 sum2 = pack2(0.f, 0.f);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t pk[32];
-#pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            const int cch = half * 2 + cc;
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const f32x2 x2 = fma2(pack2(__uint_as_float(sr[cch][i]), __uint_as_float(sr[cch][i + 1])), c2, nmc2);
-              float p0, p1;
-              if (kEmu > 0 && emu_pair<kEmu>(i >> 1)) {
-                ex2_emu2(x2, p0, p1);
-              } else {
-                float x0, x1;
-                unpack2(x2, x0, x1);
-                p0 = ex2(x0);
-                p1 = ex2(x1);
-              }
-              sum2 = add2(sum2, pack2(p0, p1));
-              pk[cc * 16 + (i >> 1)] = pack_bf16(p0, p1);
-            }
-          }
+        auto handover = [&](int half, const uint32_t (&pk)[32]) {
           tmem_st32(t_s + half * 32, pk);  // P (bf16 pairs) over the S columns already in registers
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[2 * q + half]);
-        }
-        float sum0, sum1;
-        unpack2(sum2, sum0, sum1);
-        l = l * alpha + (sum0 + sum1);
-        m = m_new;
+        };
+        attn_softmax_tile<kHeadDim, kEmu>(t_s, t_o, c, valid, jj == 0, m, l, pend, handover, [](int) {});
       }
       // ---- end of item: the last PV has to retire, then O_q leaves TMEM so that the next item's first PV may overwrite it
       if (kTrace && ctr && warp == 4 && lane == 0 && k < 8) ctr[k * 8 + 1] = (long long)globaltimer_ns();

@@ -81,4 +81,154 @@ __device__ __forceinline__ bool emu_pair(int pair) {
   return (kEmu >= 1 && r == 6) || (kEmu >= 2 && r == 2) || (kEmu >= 3 && r == 4) || (kEmu >= 4 && r == 0);
 }
 
+// ---- one KV tile of one query row: the softmax step shared by the three schedules -------------------------------------------------
+// State per row: m = reference maximum the probabilities are expressed against (lazily updated: it only moves when the true maximum
+// ran away from it by more than 2^8), l = running sum of probabilities against m, pend = true maximum of the last tile seen.
+//
+// kAttnLag = false (the build default): the tile's row maximum is found first, then the reference is updated, then the exponentials run.
+// kAttnLag = true (-DTFX_ATTN_LAG=1, an experiment): the reference is updated from the PREVIOUS tile's maximum (known before the scores arrive), the exponentials start at
+//   once and this tile's maximum is found alongside them (FMNMX on the ALU pipe under the MUFU-bound stream) -- the ~330-cycle
+//   maximum leaves the chain S-ready -> P-ready that bounds the kernel (profiles/r1j_attn_trace.md).  Probabilities may then exceed 1
+//   by the growth of the maximum inside one tile; they are exact in fp32 / bf16 up to 2^kDanger, and a tile whose maximum jumps by
+//   more than that (never observed: RMS-normed q, k bound the scores) is redone on the exact path from the scores still in TMEM.
+//   The first tile of a row always takes the exact path.
+// `handover(half, pk)` stores 32 packed bf16 pairs (64 probabilities) over the S columns and signals the issuer.
+constexpr float kAttnRescaleThreshold = 8.0f;  // log2 units
+constexpr float kAttnDanger = 30.0f;           // log2 units
+
+template <int kHeadDim>
+__device__ __forceinline__ void attn_rescale_o(uint32_t t_o, float alpha) {
+#pragma unroll 1
+  for (int cch = 0; cch < kHeadDim / 32; ++cch) {
+    uint32_t v[32];
+    tmem_ld32(t_o + cch * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+    tmem_st32(t_o + cch * 32, v);
+  }
+  tmem_st_wait();
+}
+
+template <int kEmu>
+__device__ __forceinline__ void attn_exp_half(const uint32_t (&s0)[32], const uint32_t (&s1)[32], f32x2 c2, f32x2 nmc2, f32x2& sum2, uint32_t (&pk)[32]) {
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const uint32_t(&s)[32] = cc ? s1 : s0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const f32x2 x2 = fma2(pack2(__uint_as_float(s[i]), __uint_as_float(s[i + 1])), c2, nmc2);
+      float p0, p1;
+      if (kEmu > 0 && emu_pair<kEmu>(i >> 1)) {
+        ex2_emu2(x2, p0, p1);
+      } else {
+        float x0, x1;
+        unpack2(x2, x0, x1);
+        p0 = ex2(x0);
+        p1 = ex2(x1);
+      }
+      sum2 = add2(sum2, pack2(p0, p1));
+      pk[cc * 16 + (i >> 1)] = pack_bf16(p0, p1);
+    }
+  }
+}
+
+__device__ __forceinline__ float attn_row_max(const uint32_t (&sr)[4][32]) {
+  float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+    mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+    mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
+    mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+  }
+  return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+}
+
+__device__ __forceinline__ void attn_load_scores(uint32_t t_s, int valid, uint32_t (&sr)[4][32]) {
+  tmem_ld32(t_s + 0, sr[0]);
+  tmem_ld32(t_s + 32, sr[1]);
+  tmem_ld32(t_s + 64, sr[2]);
+  tmem_ld32(t_s + 96, sr[3]);
+  tmem_ld_wait();
+  if (valid < 128) {  // ragged last tile: keys past N score -inf -> probability 0
+#pragma unroll
+    for (int cch = 0; cch < 4; ++cch)
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (cch * 32 + i >= valid) sr[cch][i] = 0xff800000u;
+  }
+}
+
+// `first`: first tile of this row's accumulation (O holds nothing yet).  `after_max()` is a hook for trace stamps.
+#ifndef TFX_ATTN_LAG
+#define TFX_ATTN_LAG 0  // measured (profiles/r2m_attn_lag.md): correct, 1-8 % SLOWER than the exact-maximum path -> not compiled in
+#endif
+constexpr bool kAttnLag = TFX_ATTN_LAG != 0;
+
+template <int kHeadDim, int kEmu, typename Handover, typename Stamp>
+__device__ __forceinline__ void attn_softmax_tile(uint32_t t_s, uint32_t t_o, float c, int valid, bool first, float& m, float& l,
+                                                  float& pend, Handover&& handover, Stamp&& stamp) {
+  const f32x2 c2 = pack2(c, c);
+  if (kAttnLag && !first) {
+    // ---- fast path: reference from the previous tile's maximum; this tile's maximum rides along with the exponentials
+    const bool need = (pend - m) * c > kAttnRescaleThreshold;
+    const float m_new = need ? pend : m;
+    if (__any_sync(0xffffffffu, need)) {
+      const float alpha = need ? ex2((m - m_new) * c) : 1.0f;
+      attn_rescale_o<kHeadDim>(t_o, alpha);  // O holds PV(0..j-1): retired, s_full(j) flipped behind PV(j-1)
+      l *= alpha;
+      m = m_new;
+    }
+    uint32_t sr[4][32];
+    attn_load_scores(t_s, valid, sr);
+    stamp(1);
+    const float mc = m * c;
+    const f32x2 nmc2 = pack2(-mc, -mc);
+    f32x2 sum2 = pack2(0.f, 0.f);
+    uint32_t pk[32];
+    attn_exp_half<kEmu>(sr[0], sr[1], c2, nmc2, sum2, pk);
+    const float mx = attn_row_max(sr);
+    stamp(2);
+    if (!__any_sync(0xffffffffu, (mx - m) * c > kAttnDanger)) {
+      handover(0, pk);
+      stamp(3);
+      attn_exp_half<kEmu>(sr[2], sr[3], c2, nmc2, sum2, pk);
+      handover(1, pk);
+      stamp(4);
+      float sum0, sum1;
+      unpack2(sum2, sum0, sum1);
+      l += sum0 + sum1;
+      pend = mx;
+      return;
+    }
+    // a jump of more than 2^kAttnDanger inside one tile: nothing was handed over yet, S is intact in TMEM -> exact path below
+  }
+  uint32_t sr[4][32];
+  attn_load_scores(t_s, valid, sr);
+  stamp(1);
+  const float mx = attn_row_max(sr);
+  // lazy rescaling: the reference point m only moves when the true max ran away from it
+  const bool need = (mx - m) * c > kAttnRescaleThreshold;  // true on the first tile (m = -inf)
+  const float m_new = need ? mx : m;
+  const float alpha = need ? ex2((m - m_new) * c) : 1.0f;
+  if (!first && __any_sync(0xffffffffu, need)) attn_rescale_o<kHeadDim>(t_o, alpha);
+  stamp(2);
+  const float mc = m_new * c;
+  const f32x2 nmc2 = pack2(-mc, -mc);
+  f32x2 sum2 = pack2(0.f, 0.f);
+  uint32_t pk[32];
+  attn_exp_half<kEmu>(sr[0], sr[1], c2, nmc2, sum2, pk);
+  handover(0, pk);
+  stamp(3);
+  attn_exp_half<kEmu>(sr[2], sr[3], c2, nmc2, sum2, pk);
+  handover(1, pk);
+  stamp(4);
+  float sum0, sum1;
+  unpack2(sum2, sum0, sum1);
+  l = l * alpha + (sum0 + sum1);
+  m = m_new;
+  pend = mx;
+}
+
 }  // namespace tfx

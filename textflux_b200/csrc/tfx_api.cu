@@ -1690,6 +1690,7 @@ int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int
     p.out = reinterpret_cast<bf16*>(out); p.ld_out = ld_out;
     LaunchCtx c{reinterpret_cast<cudaStream_t>(stream), dev, &g_op_launches, err_};
     const int sched = q_tiles % 10, emu = (q_tiles / 10) % 10;
+    const bool trace_build = (q_tiles / 100) % 10 != 0;
     if (sched == 9 || sched == 7) {  // schedule 4 (stream) | schedule 5 (persistent stream): + 10 * emu
       static std::map<int, Attn4Workspace> ws_on;  // per device, sized for the largest head_dim
       Attn4Workspace& ws = ws_on[dev];
@@ -1701,11 +1702,11 @@ int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int
       }
       p.cta_trace = reinterpret_cast<long long*>(g_attn_cta_trace);
       if (sched == 9) launch_attention4(c, head_dim, emu, mq, mk, mv, p, ws);
-      else launch_attention5(c, head_dim, emu, mq, mk, mv, p, ws, q_tiles >= 100);
+      else launch_attention5(c, head_dim, emu, mq, mk, mv, p, ws, trace_build);
     } else if (sched == 5 || sched == 6) {  // schedule 3: 5 = whole-P hand-over, 6 = split; + 10 * emu; + 100 trace
       p.trace = reinterpret_cast<long long*>(g_attn_trace);
       p.cta_trace = reinterpret_cast<long long*>(g_attn_cta_trace);
-      launch_attention3(c, head_dim, emu, sched == 6, q_tiles >= 100, mq, mk, mv, p);
+      launch_attention3(c, head_dim, emu, sched == 6, trace_build, mq, mk, mv, p);
     } else {
       REQUIRE(false, TFX_ERR_INVALID, "attention schedule code %d unknown (5 | 6 | 7 | 9, + 10 * emu)", q_tiles);
     }
