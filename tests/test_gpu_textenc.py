@@ -68,6 +68,28 @@ def test_clip_against_transformers_golden():
     assert enc.counter("launches") == l0 and enc.cache_hits == 1 and torch.equal(again.pooler_output, out.pooler_output)
 
 
+@pytest.mark.parametrize("T", [1, 5, 16, 32, 33, 100])
+def test_short_and_ragged_sequence_lengths(T):
+    """Sequence lengths below and off the 16-row MMA block and the 32-row query block (the score tile doubles as the output staging
+    tile: T = 32 once overflowed it), two prompts, both encoders, against the CUDA-run oracle."""
+    tcfg, ccfg = to.T5_TINY, to.CLIP_TINY
+    tsd = to.init_state_dict(to.t5_spec(tcfg), 5, device="cuda")
+    csd = to.init_state_dict(to.clip_spec(ccfg), 6, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(T)
+    ids = torch.randint(2, tcfg.vocab_size, (2, T), generator=g, device="cuda")
+    out = _t5(tcfg, tsd)(ids)[0]
+    _bar(f"T5 T={T}", out, to.t5_encode({k: v.to(torch.bfloat16) for k, v in tsd.items()}, tcfg, ids), to.t5_encode(tsd, tcfg, ids))
+    if T <= ccfg.max_position_embeddings:
+        cids = torch.randint(3, ccfg.vocab_size - 2, (2, T), generator=g, device="cuda")
+        cids[0, T // 2] = ccfg.vocab_size - 1
+        cids[1, T - 1] = ccfg.vocab_size - 1
+        o = _clip(ccfg, csd, cache=False)(cids)
+        lh16, po16 = to.clip_encode({k: v.to(torch.bfloat16) for k, v in csd.items()}, ccfg, cids)
+        lh32, po32 = to.clip_encode(csd, ccfg, cids)
+        _bar(f"CLIP T={T} last_hidden_state", o.last_hidden_state, lh16, lh32)
+        _bar(f"CLIP T={T} pooler_output", o.pooler_output, po16, po32)
+
+
 def test_t5_xxl_width_vs_cuda_oracle():
     """Two layers at T5-XXL's real dimensions, 512 tokens: the shapes every GEMM and the attention kernel see in production."""
     cfg = to.T5Cfg(num_layers=2)

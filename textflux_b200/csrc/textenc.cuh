@@ -94,13 +94,15 @@ struct SmallAttnParams {
 };
 
 constexpr int kSmallAttnRows = 32;
-inline size_t small_attn_smem(int Tp) { return (size_t)kSmallAttnRows * (Tp + 8) * 4 + (size_t)kSmallAttnRows * (Tp + 16) * 2 + (size_t)2 * Tp * 4; }
+// row stride of the fp32 score tile: at least 72 floats, because the tile is reused as the [32][72] fp32 staging area of O
+__host__ __device__ inline int small_attn_lds(int Tp) { return Tp + 8 > 72 ? Tp + 8 : 72; }
+inline size_t small_attn_smem(int Tp) { return (size_t)kSmallAttnRows * small_attn_lds(Tp) * 4 + (size_t)kSmallAttnRows * (Tp + 16) * 2 + (size_t)2 * Tp * 4; }
 
 template <bool kCausal>
 __global__ void __launch_bounds__(128) small_attention_kernel(SmallAttnParams p) {
   using namespace nvcuda;
   extern __shared__ __align__(32) uint8_t sm_raw[];
-  const int Tp = p.Tp, lds = Tp + 8, ldp = Tp + 16;
+  const int Tp = p.Tp, lds = small_attn_lds(Tp), ldp = Tp + 16;
   float* S = reinterpret_cast<float*>(sm_raw);
   __nv_bfloat16* P = reinterpret_cast<__nv_bfloat16*>(sm_raw + (size_t)kSmallAttnRows * lds * 4);
   float* relv = reinterpret_cast<float*>(sm_raw + (size_t)kSmallAttnRows * lds * 4 + (size_t)kSmallAttnRows * ldp * 2);
