@@ -93,12 +93,18 @@ __global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(GnParams p) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
   const uint4* src = reinterpret_cast<const uint4*>(p.x) + (long long)b * p.HW * vecs;
-  for (long long pix = p0 + pl; pix < p1; pix += lanes) {
-    const uint4 u = __ldg(src + pix * vecs + v);
+  auto acc = [&](const uint4& u) {
     const float x[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] += x[j]; q[j] = fmaf(x[j], x[j], q[j]); }
+  };
+  long long pix = p0 + pl;
+  for (; pix + 3LL * lanes < p1; pix += 4LL * lanes) {  // four loads in flight per thread
+    const uint4 u0 = __ldg(src + pix * vecs + v), u1 = __ldg(src + (pix + lanes) * vecs + v);
+    const uint4 u2 = __ldg(src + (pix + 2LL * lanes) * vecs + v), u3 = __ldg(src + (pix + 3LL * lanes) * vecs + v);
+    acc(u0); acc(u1); acc(u2); acc(u3);
   }
+  for (; pix < p1; pix += lanes) acc(__ldg(src + pix * vecs + v));
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     red[(pl * p.C + v * 8 + j) * 2 + 0] = s[j];
@@ -115,14 +121,22 @@ __global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(GnParams p) {
   }
 }
 
-__global__ void gn_finalize_kernel(GnParams p) {
-  const int b = blockIdx.x, g = threadIdx.x;
-  if (g >= p.G) return;
+// one block of 128 threads per (group, image): a handful of independent loads per thread, then a fixed-order tree (deterministic)
+__global__ void __launch_bounds__(128) gn_finalize_kernel(GnParams p) {
+  __shared__ double red[2][4];
+  const int g = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double s = 0.0, q = 0.0;
-  for (int c = 0; c < p.nchunk; ++c) {
-    const float* o = p.partial + (((long long)b * p.nchunk + c) * p.G + g) * 2;
-    s += o[0]; q += o[1];
+  for (int c = threadIdx.x; c < p.nchunk; c += 128) {
+    const float2 o = *reinterpret_cast<const float2*>(p.partial + (((long long)b * p.nchunk + c) * p.G + g) * 2);
+    s += o.x; q += o.y;
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, d); q += __shfl_xor_sync(0xffffffffu, q, d); }
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = q; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  s = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+  q = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
   const double n = double(p.HW) * (p.C / p.G);
   const double mean = s / n;
   double var = q / n - mean * mean;
@@ -150,18 +164,24 @@ __global__ void __launch_bounds__(kGnThreads) gn_apply_kernel(GnParams p) {
   const long long total = p.HW * vecs;
   const uint4* src = reinterpret_cast<const uint4*>(p.x) + (long long)b * total;
   uint4* dst = reinterpret_cast<uint4*>(p.y) + (long long)b * total;
-  for (long long i = i0; i < total; i += (long long)gridDim.x * kGnThreads) {
-    const uint4 u = __ldg(src + i);
+  auto apply = [&](const uint4& u) {
     float x[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y), bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       x[j] = fmaf(x[j], a[j], c[j]);
-      if (p.silu) x[j] = silu(x[j]);
+      if (p.silu) x[j] = __fdividef(x[j], 1.0f + __expf(-x[j]));  // approximate division: 2 ulp in fp32, invisible after the bf16 store
     }
     uint4 o;
     o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]); o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
-    dst[i] = o;
+    return o;
+  };
+  const long long stride = (long long)gridDim.x * kGnThreads;
+  long long i = i0;
+  for (; i + 3 * stride < total; i += 4 * stride) {  // four loads in flight per thread
+    const uint4 u0 = __ldg(src + i), u1 = __ldg(src + i + stride), u2 = __ldg(src + i + 2 * stride), u3 = __ldg(src + i + 3 * stride);
+    dst[i] = apply(u0); dst[i + stride] = apply(u1); dst[i + 2 * stride] = apply(u2); dst[i + 3 * stride] = apply(u3);
   }
+  for (; i < total; i += stride) dst[i] = apply(__ldg(src + i));
 }
 
 // ---- row softmax of fp32 scores -> bf16 probabilities: P = softmax(scale * S) (F.scaled_dot_product_attention of the mid block) ---

@@ -149,11 +149,11 @@ struct tfx_vae {
     p.x = x; p.y = y; p.B = B; p.C = C; p.G = G; p.HW = HW;
     p.gamma = Wt(name + ".weight", 1, C).ptr; p.beta = Wt(name + ".bias", 1, C).ptr;
     p.eps = 1e-6f; p.silu = act ? 1 : 0; p.partial = gn_partial; p.stats = gn_stats;
-    const long long want = (HW + 255) / 256;
-    p.nchunk = (int)std::max<long long>(1, std::min<long long>(want, std::min<long long>(1024, 2LL * num_sms(device) / std::max(1, B) + 1)));
+    const long long want = (HW + 63) / 64;  // at least 64 pixels per chunk
+    p.nchunk = (int)std::max<long long>(1, std::min<long long>(want, std::min<long long>(2048, 8LL * num_sms(device) / std::max(1, B))));
     REQUIRE((long long)B * p.nchunk * G * 2 <= (1 << 20) && (long long)B * G * 2 <= 8192, TFX_ERR_INVALID, "GroupNorm workspace too small");
     gn_partial_kernel<<<dim3(p.nchunk, B), kGnThreads, 0, stream>>>(p);
-    gn_finalize_kernel<<<B, ((G + 31) / 32) * 32, 0, stream>>>(p);
+    gn_finalize_kernel<<<dim3(G, B), 128, 0, stream>>>(p);
     const long long vec_total = HW * (C / 8);
     const int blocks = (int)std::max<long long>(1, std::min<long long>((vec_total + kGnThreads - 1) / kGnThreads, 8LL * num_sms(device)));
     gn_apply_kernel<<<dim3(blocks, B), kGnThreads, 0, stream>>>(p);
