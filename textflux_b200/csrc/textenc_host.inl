@@ -45,7 +45,7 @@ struct tfx_textenc {
   }
   void linear(const bf16* x, long long rows, int K, bf16* y, int N, const std::string& wname, const bf16* bias, int mode, const bf16* res) {
     const Weight& wt = Wt(wname, N, K);
-    const int cg = 2, bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64);
+    const int bn = N >= 256 ? 256 : (N >= 128 ? 128 : 64), cg = bn == 128 ? 1 : 2;  // 128-wide outputs: single-CTA tiles (vae_host.inl)
     CUtensorMap ma = make_map_2d(err_, x, rows, K, K, 128);
     CUtensorMap mb = make_map_2d(err_, wt.ptr, N, K, K, bn / cg);
     GemmParams p;

@@ -96,6 +96,11 @@ struct tfx_vae {
 
   // ---- layers -------------------------------------------------------------------------------------------------------------
   static int tile_n(int Cout) { return Cout >= 256 ? 256 : (Cout >= 128 ? 128 : 64); }
+  // An SS-mode MMA re-reads its 128 x 16 A operand (4 KB) from shared memory at ~64 B/cycle whatever N is (profiles/r2s_attn_dbuf.md):
+  // a CTA pair on a 256 x 128 tile does 32 cycles of math per 64-cycle read (ncu: tensor pipe 35-38 % on the Cout = 128 layers), a
+  // single CTA on 128 x 128 does 64 -- but then fetches 32 KB of operands per k-block from the L2, twice what the L2 feeds an SM.
+  // Measured at 1024 x 1152 (profiles/r2t_final.md): 128-wide outputs 8 % faster on single-CTA tiles, 64-wide ones 30 % slower.
+  static int cta_group_for(int bn) { return bn == 128 ? 1 : 2; }
 
   // y[B, Ho, Wo, Cout] = conv3x3(x[B, H, W, Cin]) + bias (+ res): stride 1 pad 1, or stride 2 with Downsample2D's (0,1,0,1) padding
   void conv3x3(const bf16* x, int B, int H, int W, int Cin, bf16* y, int Cout, const std::string& name, bool stride2, const bf16* res) {
@@ -104,7 +109,7 @@ struct tfx_vae {
     const Weight& bs = Wt(name + ".bias", 1, Cout);
     const int Ho = stride2 ? H / 2 : H, Wo = stride2 ? W / 2 : W;
     REQUIRE(!stride2 || (H % 2 == 0 && W % 2 == 0), TFX_ERR_INVALID, "stride-2 convolution needs even height and width (%d x %d)", H, W);
-    const int bn = tile_n(Cout), cg = 2;
+    const int bn = tile_n(Cout), cg = cta_group_for(bn);
     CUtensorMap mb = make_map_2d(err_, wt.ptr, Cout, 9LL * Cin, 9LL * Cin, bn / cg);
     GemmParams p;
     memset(&p, 0, sizeof p);
@@ -129,7 +134,7 @@ struct tfx_vae {
   // y[rows, N] = epilogue(x[rows, K] W^T + bias): 1x1 convolutions and the attention projections on NHWC rows
   void linear(const bf16* x, long long lda, long long rows, int K, bf16* y, long long ldo, int N, const bf16* wt, const bf16* bias, int mode,
               const bf16* res, long long ldw = 0) {
-    const int bn = tile_n(N), cg = 2;
+    const int bn = tile_n(N), cg = cta_group_for(bn);
     CUtensorMap ma = make_map_2d(err_, x, rows, K, lda, 128);
     CUtensorMap mb = make_map_2d(err_, wt, N, K, ldw ? ldw : K, bn / cg);
     GemmParams p;
