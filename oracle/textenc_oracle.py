@@ -69,7 +69,8 @@ def t5_spec(cfg: T5Cfg) -> List[Tuple[str, Tuple[int, ...], str]]:
     out = [("shared.weight", (cfg.vocab_size, cfg.d_model), "e")]
     for i in range(cfg.num_layers):
         a, f = f"encoder.block.{i}.layer.0", f"encoder.block.{i}.layer.1"
-        for m in ("q", "k", "v"):
+        out.append((f"{a}.SelfAttention.q.weight", (inner, cfg.d_model), "wq"))
+        for m in ("k", "v"):
             out.append((f"{a}.SelfAttention.{m}.weight", (inner, cfg.d_model), "w"))
         out.append((f"{a}.SelfAttention.o.weight", (cfg.d_model, inner), "w"))
         if i == 0:
@@ -100,14 +101,18 @@ def clip_spec(cfg: ClipCfg) -> List[Tuple[str, Tuple[int, ...], str]]:
 
 
 def init_state_dict(spec, seed: int, dtype=torch.float32, device="cpu") -> Dict[str, Tensor]:
-    """Synthetic weights: embeddings N(0,1) (T5) / N(0, 0.02^2)-ish scale kept O(1) after the first norm, linears N(0, 1/fan_in),
-    biases N(0, 0.02^2), norm weights 1 + N(0, 0.1^2), relative-attention bias N(0, 0.5^2)."""
+    """Synthetic weights: embeddings N(0,1), linears N(0, 1/fan_in), biases N(0, 0.02^2), norm weights 1 + N(0, 0.1^2),
+    relative-attention bias N(0, 0.5^2).  T5 does not scale its scores by d_kv^-0.5 (the factor lives in the trained weights; T5's own
+    initialiser gives q a std of (d_model * d_kv)^-0.5): its q projections get that extra d_kv^-0.5 here, otherwise the logits have a
+    std of 8, every softmax is one-hot and 24 layers amplify bf16 rounding into noise (reference bf16-vs-fp32 rel-L2 0.9)."""
     sd = {}
     for idx, (name, shape, kind) in enumerate(spec):
         g = torch.Generator(device=device).manual_seed(seed * 100003 + idx)
         t = torch.randn(shape, generator=g, device=device, dtype=torch.float32)
         if kind == "w":
             t = t * (1.0 / shape[1]) ** 0.5
+        elif kind == "wq":
+            t = t * (1.0 / (shape[1] * 64)) ** 0.5
         elif kind == "b":
             t = t * 0.02
         elif kind == "g":

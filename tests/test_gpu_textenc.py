@@ -104,6 +104,24 @@ def test_t5_xxl_width_vs_cuda_oracle():
     _bar("T5-XXL width, 2 layers, T=512", out, to.t5_encode(sd16, cfg, ids), to.t5_encode(sd32, cfg, ids))
 
 
+def test_t5_xxl_full_depth_vs_cuda_oracle():
+    """The whole T5-XXL encoder (24 layers, 4.76 B parameters), one 512-token prompt padded the way the pipeline pads it."""
+    cfg = to.T5_XXL
+    sd16 = to.init_state_dict(to.t5_spec(cfg), 7, dtype=torch.bfloat16, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ids = torch.randint(2, cfg.vocab_size, (1, 512), generator=g, device="cuda")
+    ids[:, 70:] = 0
+    ids[:, 69] = 1
+    enc = _t5(cfg, sd16)
+    out = enc(ids)[0]
+    ref16 = to.t5_encode(sd16, cfg, ids)
+    del enc
+    sd32 = {k: v.float() for k, v in sd16.items()}
+    del sd16
+    torch.cuda.empty_cache()
+    _bar("T5-XXL, 24 layers, T=512", out, ref16, to.t5_encode(sd32, cfg, ids))
+
+
 def test_clip_l_vs_cuda_oracle():
     """The whole CLIP-L text tower (12 layers, 768 wide), T = 77 (not a multiple of the 16-row MMA block), two prompts."""
     cfg = to.CLIP_L

@@ -80,6 +80,25 @@ def test_vae_flux_dims_vs_cuda_oracle(H, W, B):
     _bar(f"decode {B}x{H}x{W}", img, vo.decode(sd16, cfg, z), vo.decode(sd32, cfg, z.float()))
 
 
+def test_vae_headline_canvas_vs_cuda_oracle():
+    """BASELINE's headline canvas (1024 x 1152: 128 x 144 latents, 18 432 mid-block tokens) through encode and decode at FLUX's VAE
+    dimensions, against the oracle on CUDA in bf16 (what pipe.vae runs today) and in fp32."""
+    cfg = vo.FLUX_VAE
+    sd32 = {k: v.cuda() for k, v in vo.init_state_dict(cfg, seed=31).items()}
+    sd16 = {k: v.to(torch.bfloat16) for k, v in sd32.items()}
+    g = torch.Generator(device="cuda").manual_seed(2176)
+    H, W = 1024, 1152
+    image = (torch.rand(1, 3, H, W, generator=g, device="cuda") * 2 - 1).to(torch.bfloat16)
+    z = torch.randn(1, 16, H // 8, W // 8, generator=g, device="cuda").to(torch.bfloat16)
+    vae = _engine(cfg, {k: v.cpu() for k, v in sd32.items()})
+    m = vae.encode(image).latent_dist.parameters
+    _bar("encode 1024x1152", m, vo.encode_moments(sd16, cfg, image), vo.encode_moments(sd32, cfg, image.float()))
+    img = vae.decode(z, return_dict=False)[0]
+    ref16 = vo.decode(sd16, cfg, z)
+    torch.cuda.empty_cache()
+    _bar("decode 1024x1152", img, ref16, vo.decode(sd32, cfg, z.float()))
+
+
 def test_vae_rejects_what_it_does_not_implement():
     from textflux_b200.vae import B200AutoencoderKL
     cfg = vo.SMALL_VAE
