@@ -192,6 +192,7 @@ int tfx_textenc_get_counter(tfx_textenc_handle h, const char* key, int64_t* valu
 int tfx_textenc_encode(tfx_textenc_handle h, const int32_t* input_ids, int32_t B, int32_t T, const int32_t* rel_bucket_lut,
                        void* last_hidden_state, const int32_t* pooled_index, void* pooled_out, void* stream) {
   API_BEGIN(h)
+  NvtxRange nvtx_("tfx_textenc_encode");
   REQUIRE(h && input_ids && last_hidden_state && B >= 1, TFX_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);

@@ -2,6 +2,7 @@
 // sequence of FluxTransformer2DModel.forward (transformer_flux.py:1028-1212) and CUDA-graph replay of it.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -31,6 +32,15 @@ typedef __nv_bfloat16 bf16;
 namespace {
 
 thread_local std::string g_last_error;
+
+// NVTX range over a host-side scope (header-only nvtx3: a no-op unless a profiler is attached).  Every C-ABI entry point of the
+// hot path and the sections of the launch sequence carry one, so a timeline shows call -> section -> kernels.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct Fail {
   int code;
@@ -876,6 +886,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
   };
 
   // --- positional table (pos_embed(cat(txt_ids, img_ids)), transformer_flux.py:1114-1115)
+  NvtxRange nvtx_fwd("enqueue_forward");
   {
     RopeParams rp;
     rp.txt_ids = ids_txt; rp.img_ids = ids_img; rp.T = T; rp.S = S;
@@ -945,6 +956,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
 
   // --- 19 x FluxTransformerBlock (transformer_flux.py:794-841); chunk order shift,scale,gate (msa) shift,scale,gate (mlp)
   for (int i = 0; i < L; ++i) {
+    NvtxRange nvtx_blk(name("double block %d", i, "").c_str());
     const char* sfx[2] = {"_c", "_x"};
     lp.shift0 = mod_double(i, 1, 0); lp.scale0 = mod_double(i, 1, 1);
     lp.shift1 = mod_double(i, 0, 0); lp.scale1 = mod_double(i, 0, 1);
@@ -999,6 +1011,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
   // --- 38 x FluxSingleTransformerBlock (transformer_flux.py:715-739) on the joint [text;image] rows (the cat of
   //     :1160 is the row layout of `hidden` itself); chunk order shift, scale, gate
   for (int j = 0; j < Ls; ++j) {
+    NvtxRange nvtx_blk(name("single block %d", j, "").c_str());
     lp.shift0 = lp.shift1 = mod_single(j, 0);
     lp.scale0 = lp.scale1 = mod_single(j, 1);
     launch_ln_modulate(c, lp);
@@ -1344,6 +1357,7 @@ int tfx_forward(tfx_handle h, const void* hidden_states, const void* encoder_hid
                 const void* timestep_bf16, const void* guidance_f32, const void* img_ids, const void* txt_ids,
                 void* out_sample, void* stream) {
   API_BEGIN(h)
+  NvtxRange nvtx_("tfx_forward");
   REQUIRE(h && hidden_states && out_sample, TFX_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
@@ -1359,6 +1373,7 @@ int tfx_step(tfx_handle h, const void* latents_in, const void* cond, const void*
              const void* timestep_bf16, const void* guidance_f32, const void* img_ids, const void* txt_ids, float sigma,
              float sigma_next, void* latents_out, void* noise_pred_out, void* stream) {
   API_BEGIN(h)
+  NvtxRange nvtx_("tfx_step");
   REQUIRE(h && latents_in && cond && latents_out, TFX_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
@@ -1386,6 +1401,7 @@ int tfx_step(tfx_handle h, const void* latents_in, const void* cond, const void*
 int tfx_set_schedule(tfx_handle h, const void* timesteps_bf16, int32_t n_steps, const void* guidance_f32, const void* pooled,
                      void* stream) {
   API_BEGIN(h)
+  NvtxRange nvtx_("tfx_set_schedule");
   REQUIRE(h && timesteps_bf16 && pooled && n_steps > 0, TFX_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(h->device));
   if (h->B == 0 && h->pB > 0) h->prepare(h->pB, h->pS, h->pT);
@@ -1429,6 +1445,7 @@ int tfx_step_scheduled(tfx_handle h, int32_t step_index, const void* latents_in,
                        const void* encoder_hidden_states, const void* img_ids, const void* txt_ids, float sigma, float sigma_next,
                        void* latents_out, void* noise_pred_out, void* stream) {
   API_BEGIN(h)
+  NvtxRange nvtx_("tfx_step_scheduled");
   REQUIRE(h && latents_in && cond && latents_out, TFX_ERR_INVALID, "null argument");
   REQUIRE(h->mod_table && step_index >= 0 && step_index < h->sched_steps, TFX_ERR_STATE,
           "step %d outside the schedule set by tfx_set_schedule (%d steps)", step_index, h->sched_steps);

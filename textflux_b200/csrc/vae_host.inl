@@ -393,6 +393,7 @@ int tfx_vae_get_counter(tfx_vae_handle h, const char* key, int64_t* value) {
 
 int tfx_vae_encode(tfx_vae_handle h, const void* image, int32_t image_is_f32, int32_t B, int32_t H, int32_t W, void* moments_out, void* stream) {
   API_BEGIN(h)
+  NvtxRange nvtx_("tfx_vae_encode");
   REQUIRE(h && image && moments_out && B >= 1, TFX_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
@@ -412,6 +413,7 @@ int tfx_vae_encode(tfx_vae_handle h, const void* image, int32_t image_is_f32, in
 
 int tfx_vae_decode(tfx_vae_handle h, const void* latents, int32_t B, int32_t lh, int32_t lw, void* image_out, void* stream) {
   API_BEGIN(h)
+  NvtxRange nvtx_("tfx_vae_decode");
   REQUIRE(h && latents && image_out && B >= 1 && lh >= 1 && lw >= 1, TFX_ERR_INVALID, "bad argument");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
