@@ -307,7 +307,7 @@ def run_ours(args, name):
     eng = B200FluxTransformer(cfg, getter, device=dev, **eng_kw)  # library defaults unless overridden on the command line
     for key, val in (("use_pdl", args.pdl), ("attn_variant", args.attn_variant or -1), ("attn_emu", args.attn_emu),
                      ("gemm_l2_hints", args.l2_hints), ("gemm_narrow_tiles", args.narrow_tiles), ("gemm_m_band", args.m_band)):
-        if val >= 0:
+        if val >= 0 or (key == "gemm_m_band" and val <= -100):
             eng.set_option(key, val)
 
     def barrier():

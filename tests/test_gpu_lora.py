@@ -187,7 +187,7 @@ def test_linear_with_side_adapter_matches_unfused_math(M, N, K, rank, cta_group)
     assert _rel(plain, base) < 4e-3
 
 
-@pytest.mark.parametrize("band", [1, 3, 5, 40])
+@pytest.mark.parametrize("band", [1, 3, 5, 40, -1, -3, -7, -40])
 @pytest.mark.parametrize("M,N,K", [(2560, 3072, 1024), (1300, 640, 256), (5120, 3072, 512)])
 def test_banded_tile_order_is_bit_identical(M, N, K, band):
     """GemmParams::m_band only permutes which CTA pair computes which tile."""

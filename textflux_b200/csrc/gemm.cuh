@@ -75,7 +75,7 @@ struct GemmParams {
   const float* dt_ptr;  // EULER: device scalar float(bf16(sigma_next - sigma))
   int debug_flags;      // bit 0: A loads with L2 evict_last, bit 1: B (weight) loads with L2 evict_first
   ConvGeom conv;        // conv.mode != 0: g[0].M = B * H * W output pixels, K = 9 * Cin, tmA0 is the image map (see ConvGeom)
-  int m_band;           // tile order: 0 = M-fastest over all M tiles (a wave spans every M tile and a few N tiles: each weight tile
+  int m_band;           // tile order (b < 0: N bands of -b tiles, see gemm_tile_coords): 0 = M-fastest over all M tiles (a wave spans every M tile and a few N tiles: each weight tile
                         // is fetched once, A must stay in L2); b > 0 = bands of b M tiles, inside a band M-fastest over all N tiles
                         // (a wave spans b M tiles x all N tiles: for wide-K GEMMs whose A is larger than the L2)
   int k_ext;            // 0 | 64: one extra k-block behind the K of A whose operands come from the extension descriptors
@@ -278,7 +278,15 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, int grp,
 
 // tile index -> (M tile, N tile) under GemmParams::m_band
 __device__ __forceinline__ void gemm_tile_coords(int t, int MT, int NT, int band, int& mi, int& ni) {
-  if (band <= 0 || band >= MT) { mi = t % MT; ni = t / MT; return; }
+  if (band < 0) {  // N bands of -band tiles: inside a band N-fastest over all M tiles (the band of W stays in L2, A streams once per band)
+    const int bw = -band, per = MT * bw;
+    const int nb = t / per, r = t - nb * per;
+    const int cols = min(bw, NT - nb * bw);
+    mi = r / cols;
+    ni = nb * bw + (r - mi * cols);
+    return;
+  }
+  if (band == 0 || band >= MT) { mi = t % MT; ni = t / MT; return; }
   const int per = band * NT;
   const int b = t / per, r = t - b * per;
   const int rows = min(band, MT - b * band);

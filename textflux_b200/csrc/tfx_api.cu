@@ -698,6 +698,7 @@ struct tfx_model {
   // tiles is one wave -- each wave then streams band x 256 rows of A once and the whole weight, instead of the whole of A.
   // Measured in the step (profiles/r2h_band.md): cfg3 72.05 -> 71.4 ms, cfg5 142.0 -> 138.6 ms, DRAM traffic 81.6 -> 74.5 GB.
   int band_for(long long rows, long long K, int Nn, int bn) const {
+    if (gemm_m_band <= -100) return gemm_m_band + 100;  // experiment: N bands of (-100 - value) tiles
     if (gemm_m_band >= 0) return gemm_m_band;
     if (rows * K * 2 <= (64LL << 20)) return 0;
     const int units = num_sms(device) / gemm_cta_group, nt = (Nn + bn - 1) / bn;
@@ -1189,7 +1190,7 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
   } else if (k == "gemm_narrow_tiles") {
     h->gemm_narrow_tiles = value != 0;  // weight-side descriptors are keyed by tile width: nothing to rebuild
   } else if (k == "gemm_m_band") {
-    REQUIRE(value >= -1 && value <= 64, TFX_ERR_INVALID, "gemm_m_band must be -1 (per shape) or 0..64");
+    REQUIRE(value >= -164 && value <= 64, TFX_ERR_INVALID, "gemm_m_band must be -1 (per shape), 0..64 (M bands) or -100 - n (N bands of n tiles)");
     h->gemm_m_band = (int)value;
   } else if (k == "gemm_l2_hints") {
     REQUIRE(value >= 0 && value <= 3, TFX_ERR_INVALID, "gemm_l2_hints must be 0..3");

@@ -27,7 +27,7 @@ def main():
     eng = B200FluxTransformer(cfg, synthetic_getter(cfg, 1234, dev), device=dev)
     if args.attn_variant >= 0:
         eng.set_option("attn_variant", args.attn_variant)
-    if args.m_band >= 0:
+    if args.m_band >= 0 or args.m_band <= -100:
         eng.set_option("gemm_m_band", args.m_band)
     inp = bench.Inputs(args.workload, dev, 0, 1)
     eng.set_schedule(inp.ts, inp.guidance, inp.pooled_b, inp.S, inp.T)
