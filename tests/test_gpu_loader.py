@@ -92,3 +92,69 @@ def test_lora_hot_swap_on_a_live_engine(tmp_path):
     assert torch.equal(with_lora, fresh) and not torch.equal(with_lora, base)
     eng.unload_lora_weights(sd.__getitem__)
     assert torch.equal(_run(eng, inp, t, gd), base)
+
+
+def test_pipeline_directory_loads_every_stage(tmp_path):
+    """loader.load_components on a FluxFillPipeline-shaped directory: each engine equals the one built from the state dict."""
+    from oracle import textenc_oracle as to
+    from oracle import vae_oracle as vo
+    from textflux_b200 import B200AutoencoderKL, B200CLIPTextEncoder, B200FluxTransformer, B200T5Encoder
+    from textflux_b200 import loader as ld
+
+    def write(sub, sd, config, single, shards=1, index=None):
+        d = tmp_path / sub
+        d.mkdir()
+        json.dump(config, open(d / "config.json", "w"))
+        sd = {k: v.to(torch.bfloat16) for k, v in sd.items()}
+        if shards == 1:
+            ld.save_safetensors(sd, str(d / single))
+        else:
+            names, wm = sorted(sd), {}
+            for i in range(shards):
+                fn = single.replace(".safetensors", f"-{i + 1:05d}-of-{shards:05d}.safetensors")
+                ld.save_safetensors({k: sd[k] for k in names[i::shards]}, str(d / fn))
+                wm.update({k: fn for k in names[i::shards]})
+            json.dump({"metadata": {}, "weight_map": wm}, open(d / index, "w"))
+        return sd
+
+    cfg = fo.TINY
+    sd_t = write("transformer", fo.init_state_dict(cfg, seed=31, dtype=torch.bfloat16), dict(cfg.to_dict(), _class_name="FluxTransformer2DModel"),
+                 ld.SAFETENSORS_WEIGHTS_NAME)
+    vcfg = vo.SMALL_VAE
+    sd_v = write("vae", vo.init_state_dict(vcfg, seed=5), dict(vcfg.reference_kwargs(), _class_name="AutoencoderKL"), ld.SAFETENSORS_WEIGHTS_NAME)
+    ccfg, tcfg = to.CLIP_TINY, to.T5_TINY
+    sd_c = write("text_encoder", to.init_state_dict(to.clip_spec(ccfg), 11), dict(ccfg.to_dict(), hidden_act="quick_gelu", model_type="clip_text_model",
+                                                                                  architectures=["CLIPTextModel"]), ld.TRANSFORMERS_WEIGHTS_NAME)
+    sd_5 = write("text_encoder_2", to.init_state_dict(to.t5_spec(tcfg), 12), dict(tcfg.to_dict(), feed_forward_proj="gated-gelu", model_type="t5",
+                                                                                  architectures=["T5EncoderModel"]),
+                 ld.TRANSFORMERS_WEIGHTS_NAME, shards=2, index=ld.TRANSFORMERS_INDEX_NAME)
+    (tmp_path / "scheduler").mkdir()
+    json.dump({"_class_name": "FlowMatchEulerDiscreteScheduler", "_diffusers_version": "0.32.0", "base_image_seq_len": 256, "base_shift": 0.5,
+               "max_image_seq_len": 4096, "max_shift": 1.15, "num_train_timesteps": 1000, "shift": 3.0, "use_dynamic_shifting": True,
+               "some_future_key": 1}, open(tmp_path / "scheduler" / "scheduler_config.json", "w"))
+
+    parts = ld.load_components(str(tmp_path), device="cuda:0")
+    assert set(parts) == {"transformer", "vae", "text_encoder", "text_encoder_2", "scheduler"}
+    assert isinstance(parts["transformer"], B200FluxTransformer) and isinstance(parts["vae"], B200AutoencoderKL)
+    assert isinstance(parts["text_encoder"], B200CLIPTextEncoder) and isinstance(parts["text_encoder_2"], B200T5Encoder)
+    assert parts["scheduler"].config["shift"] == 3.0 and parts["scheduler"].config["use_dynamic_shifting"] is True
+
+    cuda = lambda sd: {k: v.cuda() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(4)
+    ids_c = torch.randint(0, ccfg.vocab_size - 1, (2, 77), generator=g)
+    ids_c[:, -1] = ccfg.vocab_size - 1
+    ref_c = B200CLIPTextEncoder(dict(ccfg.to_dict(), hidden_act="quick_gelu"), cuda(sd_c).__getitem__, device="cuda:0")
+    a, b = parts["text_encoder"](ids_c.cuda()), ref_c(ids_c.cuda())
+    assert torch.equal(a[0], b[0]) and torch.equal(a.pooler_output, b.pooler_output)
+    ids_5 = torch.randint(0, tcfg.vocab_size, (2, 64), generator=g)
+    ref_5 = B200T5Encoder(dict(tcfg.to_dict(), feed_forward_proj="gated-gelu"), cuda(sd_5).__getitem__, device="cuda:0")
+    assert torch.equal(parts["text_encoder_2"](ids_5.cuda())[0], ref_5(ids_5.cuda())[0])
+    ref_v = B200AutoencoderKL.from_state_dict(vcfg.reference_kwargs(), cuda(sd_v), device="cuda:0")
+    x = torch.randn(1, 3, 64, 96, generator=g).to(torch.bfloat16).cuda()
+    za, zb = parts["vae"].encode(x).latent_dist.mode(), ref_v.encode(x).latent_dist.mode()
+    assert torch.equal(za, zb) and torch.equal(parts["vae"].decode(za).sample, ref_v.decode(zb).sample)
+    ref_t = B200FluxTransformer.from_state_dict(cfg.to_dict(), sd_t, device="cuda:0")
+    inp = {k: v.cuda() for k, v in fo.synthetic_inputs(cfg, 8, 8, 16, batch=1, seed0=500).items()}
+    t, gd = (torch.tensor([700.0]).to(torch.bfloat16) / 1000).cuda(), torch.full([1], 30.0).cuda()
+    assert torch.equal(_run(parts["transformer"], inp, t, gd), _run(ref_t, inp, t, gd))
+    torch.cuda.synchronize()

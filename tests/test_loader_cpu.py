@@ -142,3 +142,34 @@ def test_lora_hot_swap_repacks_only_touched_matrices_bit_exactly():
     assert all(torch.equal(P[k], want[k]) for k in want)
     repack_modules(cfg, sd.__getitem__, P, lora_modules(l2))
     assert all(torch.equal(P[k], base[k]) for k in base)
+
+
+def test_checkpoint_resolves_transformers_file_names(tmp_path):
+    """Text-encoder directories use transformers' names (model.safetensors / model.safetensors.index.json)."""
+    import json
+    from textflux_b200 import loader as ld
+    g = torch.Generator().manual_seed(3)
+    sd = {f"encoder.block.{i}.w": torch.randn(4, 8, generator=g).to(torch.bfloat16) for i in range(4)}
+    one = tmp_path / "one"; one.mkdir()
+    ld.save_safetensors(sd, str(one / ld.TRANSFORMERS_WEIGHTS_NAME))
+    json.dump({"model_type": "t5"}, open(one / ld.CONFIG_NAME, "w"))
+    ck = ld.Checkpoint(str(one))
+    assert sorted(ck.keys()) == sorted(sd) and ck.config == {"model_type": "t5"}
+    assert all(torch.equal(ck.getter()(k), v) for k, v in sd.items())
+    ck.close()
+    two = tmp_path / "two"; two.mkdir()
+    names = sorted(sd)
+    wm = {}
+    for i, part in enumerate([names[:1], names[1:]]):
+        fn = f"model-{i + 1:05d}-of-00002.safetensors"
+        ld.save_safetensors({k: sd[k] for k in part}, str(two / fn))
+        wm.update({k: fn for k in part})
+    json.dump({"metadata": {}, "weight_map": wm}, open(two / ld.TRANSFORMERS_INDEX_NAME, "w"))
+    ck = ld.Checkpoint(str(two))
+    assert all(torch.equal(ck.getter()(k), v) for k, v in sd.items())
+    ck.close()
+    empty = tmp_path / "empty"; empty.mkdir()
+    with pytest.raises(FileNotFoundError):
+        ld.Checkpoint(str(empty))
+    with pytest.raises(ValueError, match="config"):
+        ld.load_text_encoder(str(two))  # weights but no config.json: refused before any device work

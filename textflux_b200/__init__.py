@@ -8,7 +8,8 @@ Public surface (mirrors what the reference pipeline touches)
     B200AutoencoderKL             drop-in for AutoencoderKL on `pipe.vae` (encode / decode)
     B200T5Encoder, B200CLIPTextEncoder   drop-ins for T5EncoderModel / CLIPTextModel on `pipe.text_encoder_2` / `pipe.text_encoder`
     conditioning                  pack/unpack/mask-pack kernels mirroring FluxFillPipeline._pack_latents & co
-    loader                        safetensors / LoRA files straight into the packed weight layout
+    loader                        safetensors / LoRA files straight into the packed weight layout (transformer, VAE, prompt encoders:
+                                  load_transformer / load_vae / load_text_encoder / load_components)
 """
 from .engine import (B200FlowMatchEulerScheduler, B200FluxTransformer, B200StochasticRFOvershotScheduler,  # noqa: F401
                      FrozenConfig, attach, calculate_shift)

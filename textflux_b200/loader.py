@@ -29,6 +29,8 @@ CONFIG_NAME = "config.json"                                                   # 
 SAFETENSORS_WEIGHTS_NAME = "diffusion_pytorch_model.safetensors"              # :34
 SAFE_WEIGHTS_INDEX_NAME = "diffusion_pytorch_model.safetensors.index.json"    # :35
 LORA_WEIGHT_NAME_SAFE = "pytorch_lora_weights.safetensors"                    # loaders/lora_base.py
+TRANSFORMERS_WEIGHTS_NAME = "model.safetensors"                               # transformers' names for the two text encoders
+TRANSFORMERS_INDEX_NAME = "model.safetensors.index.json"
 
 _DTYPES = {"BF16": torch.bfloat16, "F16": torch.float16, "F32": torch.float32, "F64": torch.float64, "I64": torch.int64,
            "I32": torch.int32, "I16": torch.int16, "I8": torch.int8, "U8": torch.uint8, "BOOL": torch.bool}
@@ -126,23 +128,27 @@ def save_safetensors(tensors: Dict[str, torch.Tensor], path: str, metadata: Opti
 
 
 class Checkpoint:
-    """A transformer checkpoint directory (single file or shards + index) or a single .safetensors file."""
+    """A checkpoint directory (single file or shards + index, under diffusers' or transformers' file names) or a single
+    .safetensors file."""
 
     def __init__(self, path: str):
         self.files: Dict[str, SafetensorsFile] = {}
         self.where: Dict[str, str] = {}
         if os.path.isdir(path):
-            index = os.path.join(path, SAFE_WEIGHTS_INDEX_NAME)
-            single = os.path.join(path, SAFETENSORS_WEIGHTS_NAME)
-            if os.path.exists(index):
-                with open(index) as f:
-                    wm = json.load(f)["weight_map"]
-                for name, fn in wm.items():
-                    self.where[name] = os.path.join(path, fn)
-            elif os.path.exists(single):
-                self._add(single)
+            for index_name, single_name in ((SAFE_WEIGHTS_INDEX_NAME, SAFETENSORS_WEIGHTS_NAME), (TRANSFORMERS_INDEX_NAME, TRANSFORMERS_WEIGHTS_NAME)):
+                index, single = os.path.join(path, index_name), os.path.join(path, single_name)
+                if os.path.exists(index):
+                    with open(index) as f:
+                        wm = json.load(f)["weight_map"]
+                    for name, fn in wm.items():
+                        self.where[name] = os.path.join(path, fn)
+                    break
+                if os.path.exists(single):
+                    self._add(single)
+                    break
             else:
-                raise FileNotFoundError(f"{path}: neither {SAFE_WEIGHTS_INDEX_NAME} nor {SAFETENSORS_WEIGHTS_NAME} found")
+                raise FileNotFoundError(f"{path}: no {SAFE_WEIGHTS_INDEX_NAME}, {SAFETENSORS_WEIGHTS_NAME}, {TRANSFORMERS_INDEX_NAME} "
+                                        f"or {TRANSFORMERS_WEIGHTS_NAME} found")
             cfg = os.path.join(path, CONFIG_NAME)
             self.config = json.load(open(cfg)) if os.path.exists(cfg) else None
         else:
@@ -218,3 +224,64 @@ def load_transformer(path: str, device="cuda", lora: Optional[str] = None, lora_
         return B200FluxTransformer(cfg, get, device=device, **engine_kw)
     finally:
         ck.close()
+
+
+def _component(path: str, config):
+    ck = Checkpoint(path)
+    cfg = config if config is not None else ck.config
+    if cfg is None:
+        ck.close()
+        raise ValueError(f"{path}: no {CONFIG_NAME} next to the weights; pass config=")
+    return ck, cfg
+
+
+def load_vae(path: str, device="cuda", config=None):
+    """B200AutoencoderKL from `<pipeline>/vae` (AutoencoderKL.from_pretrained's files: config.json +
+    diffusion_pytorch_model.safetensors)."""
+    from .vae import B200AutoencoderKL
+    ck, cfg = _component(path, config)
+    try:
+        return B200AutoencoderKL(cfg, ck.getter(device), names=ck.keys(), device=device)
+    finally:
+        ck.close()
+
+
+def load_text_encoder(path: str, device="cuda", config=None, **kw):
+    """B200CLIPTextEncoder / B200T5Encoder from `<pipeline>/text_encoder` / `<pipeline>/text_encoder_2` (transformers' files:
+    config.json + model.safetensors or its shards); the class follows config.json's `model_type` / `architectures`."""
+    from .text_encoders import B200CLIPTextEncoder, B200T5Encoder
+    ck, cfg = _component(path, config)
+    try:
+        kind = str(cfg.get("model_type", "")) + " ".join(cfg.get("architectures") or [])
+        if "t5" in kind.lower():
+            return B200T5Encoder(cfg, ck.getter(device), device=device, **kw)
+        if "clip" in kind.lower():
+            return B200CLIPTextEncoder(cfg, ck.getter(device), device=device, **kw)
+        raise ValueError(f"{path}: config.json names neither a T5 nor a CLIP text encoder ({kind!r})")
+    finally:
+        ck.close()
+
+
+def load_components(root: str, device="cuda", lora: Optional[str] = None, lora_scale: float = 1.0, **engine_kw) -> Dict[str, object]:
+    """Every device stage of a FluxFillPipeline directory (model_index.json's layout: transformer/, vae/, text_encoder/,
+    text_encoder_2/, scheduler/scheduler_config.json) as engines; sub-directories that are absent are skipped.  The
+    tokenizers stay with the caller (host-side string work, out of scope)."""
+    out: Dict[str, object] = {}
+    sub = lambda n: os.path.join(root, n)
+    if os.path.isdir(sub("transformer")):
+        out["transformer"] = load_transformer(sub("transformer"), device, lora=lora, lora_scale=lora_scale, **engine_kw)
+    if os.path.isdir(sub("vae")):
+        out["vae"] = load_vae(sub("vae"), device)
+    for n in ("text_encoder", "text_encoder_2"):
+        if os.path.isdir(sub(n)):
+            out[n] = load_text_encoder(sub(n), device)
+    sc = os.path.join(sub("scheduler"), "scheduler_config.json")
+    if os.path.exists(sc):
+        from .engine import B200FlowMatchEulerScheduler, B200StochasticRFOvershotScheduler
+        import inspect
+        with open(sc) as f:
+            raw = json.load(f)
+        known = set(inspect.signature(B200FlowMatchEulerScheduler.__init__).parameters) - {"self"}
+        cls = B200StochasticRFOvershotScheduler if "Overshot" in raw.get("_class_name", "") else B200FlowMatchEulerScheduler
+        out["scheduler"] = cls(**{k: v for k, v in raw.items() if k in known})
+    return out
