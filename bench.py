@@ -306,7 +306,8 @@ def run_ours(args, name):
         eng_kw["gemm_mcast"] = args.mcast
     eng = B200FluxTransformer(cfg, getter, device=dev, **eng_kw)  # library defaults unless overridden on the command line
     for key, val in (("use_pdl", args.pdl), ("attn_variant", args.attn_variant or -1), ("attn_emu", args.attn_emu),
-                     ("gemm_l2_hints", args.l2_hints), ("gemm_narrow_tiles", args.narrow_tiles), ("gemm_m_band", args.m_band)):
+                     ("gemm_l2_hints", args.l2_hints), ("gemm_narrow_tiles", args.narrow_tiles), ("gemm_m_band", args.m_band),
+                     ("gemm_k_snake", args.k_snake)):
         if val >= 0 or (key == "gemm_m_band" and val <= -100):
             eng.set_option(key, val)
 
@@ -711,6 +712,7 @@ def main():
     ap.add_argument("--attn-variant", type=int, default=0, help="override the attention schedule")
     ap.add_argument("--attn-emu", type=int, default=-1, help="override: softmax column pairs per 8 on the FMA-pipe exp2 (0, 2, 3, 4)")
     ap.add_argument("--narrow-tiles", type=int, default=-1, help="override: allow 224-wide GEMM tiles (0/1)")
+    ap.add_argument("--k-snake", type=int, default=-1, help="override GemmParams::k_snake on the banded wide-K GEMMs (0 | 1)")
     ap.add_argument("--m-band", type=int, default=-1, help="override the tile order of the wide-K GEMMs (0 = M-fastest, b = bands of b M tiles)")
     ap.add_argument("--l2-hints", type=int, default=-1, help="override the GEMM L2 eviction hints (0..3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

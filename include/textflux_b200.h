@@ -49,7 +49,7 @@ int tfx_create(const tfx_config* cfg, int32_t device, tfx_handle* out);
 void tfx_destroy(tfx_handle h);
 /* message of the last failure on `h` (or of the last failing call without a handle when h == NULL) */
 const char* tfx_last_error(tfx_handle h);
-/* "gemm_narrow_tiles" (0|1: allow 224-wide GEMM tiles against wave quantisation), "gemm_m_band" (-1..64: tile order of the wide-K GEMMs, -1 = per shape (default), 0 = M-fastest, b = bands of b M tiles), "gemm_l2_hints" (0..3: bit 0 activations evict_last, bit 1 weights evict_first in the GEMM's TMA loads), "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (0 = per shape, schedule 3 or 5 (default); 4 | 5 = schedule 3 whole-P / split-P, 8 = schedule 4 stream, 9 = schedule 5 persistent stream), "attn_emu" (0|2|3|4), "use_graph" (0|1), "mod_cache_slots" (0..4096: device-side cache of modulation vectors keyed on the (timestep, guidance, pooled) bits tfx_forward / tfx_step receive; 0 = recompute every call), "mod_cache_reset" (drop every cached modulation vector: call after rewriting weights in place), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
+/* "gemm_narrow_tiles" (0|1: allow 224-wide GEMM tiles against wave quantisation), "gemm_m_band" (-1..64: tile order of the wide-K GEMMs, -1 = per shape (default), 0 = M-fastest, b = bands of b M tiles, -100 - n = N bands of n tiles), "gemm_k_snake" (0|1, default 0: on the banded GEMMs the tiles of every second band walk their k-blocks back to front so that consecutive bands meet in the L2), "gemm_l2_hints" (0..3: bit 0 activations evict_last, bit 1 weights evict_first in the GEMM's TMA loads), "gemm_cta_group" (1|2), "gemm_mcast" (0|2|4: CTA pairs per cluster sharing A by TMA multicast), "attn_variant" (0 = per shape, schedule 3 or 5 (default); 4 | 5 = schedule 3 whole-P / split-P, 8 = schedule 4 stream, 9 = schedule 5 persistent stream), "attn_emu" (0|2|3|4), "use_graph" (0|1), "mod_cache_slots" (0..4096: device-side cache of modulation vectors keyed on the (timestep, guidance, pooled) bits tfx_forward / tfx_step receive; 0 = recompute every call), "mod_cache_reset" (drop every cached modulation vector: call after rewriting weights in place), "use_pdl" (0|1: programmatic dependent launch between a step's kernels), "profile" (0|1: eager launches, one CUDA-event
  * pair per kernel, summed per family; resets the sums) */
 int tfx_set_option(tfx_handle h, const char* key, int64_t value);
 /* "launches": kernels launched by this handle since creation; "graph_nodes": kernel nodes in the captured step;
@@ -121,7 +121,8 @@ int tfx_step_scheduled(tfx_handle h, int32_t step_index, const void* latents_in,
 int tfx_op_linear(const void* A, int64_t lda, const void* W, const void* bias, void* out, int64_t ldo, int32_t M,
                   int32_t N, int32_t K, int32_t mode, const void* gate, const void* res, int32_t cta_group, void* stream);
 /* tfx_op_linear with the unfused-LoRA side path: Y = epilogue(A W^T + bf16(A la^T) lb^T + bias), la [64, K], lb [N, 64];
- * t_scratch [M, 64] bf16 receives bf16(A la^T).  m_band: GEMM tile order (0 = M-fastest; b > 0 = bands of b M tiles). */
+ * t_scratch [M, 64] bf16 receives bf16(A la^T).  m_band: GEMM tile order (0 = M-fastest; b > 0 = bands of b M tiles; b < 0 = N bands of -b tiles; b + 1000 / b - 1000 = the same with
+ * the k direction alternating per band, the model option "gemm_k_snake"). */
 int tfx_op_linear_lora(const void* A, int64_t lda, const void* W, const void* bias, const void* la, const void* lb, void* t_scratch,
                        void* out, int64_t ldo, int32_t M, int32_t N, int32_t K, int32_t mode, const void* gate, const void* res,
                        int32_t cta_group, int32_t m_band, void* stream);

@@ -158,3 +158,11 @@ def test_pipeline_directory_loads_every_stage(tmp_path):
     t, gd = (torch.tensor([700.0]).to(torch.bfloat16) / 1000).cuda(), torch.full([1], 30.0).cuda()
     assert torch.equal(_run(parts["transformer"], inp, t, gd), _run(ref_t, inp, t, gd))
     torch.cuda.synchronize()
+
+    from baseline import reference_arm as ra
+    if ra.available():  # the reference's own constructor accepts the engines as its registered modules
+        ra.import_reference()
+        from diffusers import FluxFillPipeline
+        pipe = FluxFillPipeline(tokenizer=None, tokenizer_2=None, **parts)
+        assert pipe.transformer is parts["transformer"] and pipe.vae is parts["vae"] and pipe.text_encoder_2 is parts["text_encoder_2"]
+        assert pipe.vae_scale_factor == 2 ** (len(vcfg.block_out_channels) - 1)

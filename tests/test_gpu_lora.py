@@ -200,6 +200,37 @@ def test_banded_tile_order_is_bit_identical(M, N, K, band):
     assert torch.equal(out, ref)
 
 
+@pytest.mark.parametrize("band", [1, 5, -1])
+@pytest.mark.parametrize("M,N,K,rank", [(5120, 3072, 4096, 0), (1300, 640, 1000, 0), (2560, 3072, 2048, 16)])
+def test_alternating_k_direction(M, N, K, rank, band):
+    """GemmParams::k_snake: the tiles of every second band accumulate their k-blocks back to front (the extension block of the LoRA
+    side path included) -- the same sum in another order, so equal to the forward walk up to fp32 accumulation order, deterministic,
+    as close to the fp32 product as the forward walk, and bit-identical to the forward walk inside the even bands."""
+    g = torch.Generator(device="cuda").manual_seed(M + K + band)
+    x = torch.randn(M, K, generator=g, device="cuda").to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    b = torch.randn(N, generator=g, device="cuda").to(torch.bfloat16)
+    la = lb = None
+    if rank:
+        la = (torch.randn(64, K, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+        la[rank:] = 0
+        lb = (torch.randn(N, 64, generator=g, device="cuda") * 0.05).to(torch.bfloat16)
+    fwd, _ = _linear_lora(x, W, b, la, lb, m_band=band)
+    snake = band + (1000 if band > 0 else -1000)
+    out, _ = _linear_lora(x, W, b, la, lb, m_band=snake)
+    again, _ = _linear_lora(x, W, b, la, lb, m_band=snake)
+    assert torch.equal(out, again)
+    assert not torch.equal(out, fwd)
+    if band > 0:  # rows of band 0 (M tiles 0 .. band - 1) sum forwards either way
+        assert torch.equal(out[: 256 * band], fwd[: 256 * band])
+    else:
+        assert torch.equal(out[:, : 192 * -band], fwd[:, : 192 * -band])  # tiles are at least 192 columns wide
+    ref = x.float() @ W.float().t() + b.float()
+    if rank:
+        ref = ref + (x.float() @ la.float().t()).to(torch.bfloat16).float() @ lb.float().t()
+    assert abs(_rel(out, ref) - _rel(fwd, ref)) < 2e-4 and _rel(out, ref) < 4e-3 and _rel(out, fwd) < 1e-3
+
+
 def test_config4_rank16_side_path_vs_unfused_reference_math():
     """Same comparison as the fold test above, through the side path: the engine computes the reference's unfused form."""
     from textflux_b200 import B200FluxTransformer

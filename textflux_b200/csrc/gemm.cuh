@@ -78,6 +78,8 @@ struct GemmParams {
   int m_band;           // tile order (b < 0: N bands of -b tiles, see gemm_tile_coords): 0 = M-fastest over all M tiles (a wave spans every M tile and a few N tiles: each weight tile
                         // is fetched once, A must stay in L2); b > 0 = bands of b M tiles, inside a band M-fastest over all N tiles
                         // (a wave spans b M tiles x all N tiles: for wide-K GEMMs whose A is larger than the L2)
+  int k_snake;          // 1: the tiles of every second band (m_band != 0) walk their k-blocks back to front, so the W slices the previous
+                        // band of tiles read last are the first ones the next band asks the L2 for (wide-K GEMMs whose operands outgrow the L2)
   int k_ext;            // 0 | 64: one extra k-block behind the K of A whose operands come from the extension descriptors
                         // (A side tmE0 / tmE1: [M, 64]; W side tmF0 / tmF1: [N, 64]).  Unfused LoRA rides here: with
                         // T = bf16(x A_lora^T) as the A extension and (alpha/r) B_lora as the W extension the accumulator holds
@@ -377,6 +379,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
     for (int t = first_tile; t < num_tiles; t += tile_step) {
       int mi, ni;
       gemm_tile_coords(t, MT, NT, p.m_band, mi, ni);
+      // direction from the tile's band, not from which CTA computes it: a given output element sums in the same order whatever the grid
+      const bool backwards = p.k_snake && (p.m_band > 0 ? ((mi / p.m_band) & 1) : p.m_band < 0 ? ((ni / -p.m_band) & 1) : 0);
       const int grp = (mi < mt0) ? 0 : 1;
       const int m0 = (grp ? mi - mt0 : mi) * Cfg::kTileM + int(cta_rank) * 128;
       const int n0 = ni * kBN + int(cta_rank) * Cfg::kBRows;
@@ -394,7 +398,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_const
         cx0 = (r % p.conv.tiles_x) * kConvPatchW;
         if (patch >= p.conv.n_patches) { cimg = 0; cy0 = p.conv.H + 64; }  // phantom half of the last pair: every pixel out of bounds
       }
-      for (int kb = 0; kb < KB; ++kb) {
+      for (int step = 0; step < KB; ++step) {
+        const int kb = backwards ? KB - 1 - step : step;  // the accumulation is order-free for the issuer: it only counts blocks
         if constexpr (kCtaGroup == 2) mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
         else mbar_wait(&empty_bar[stage], phase ^ 1);
         if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * kCtaGroup);

@@ -597,6 +597,8 @@ struct tfx_model {
                          // 8: schedule 4 (attention4.cuh): schedule 3 split-P + the last partial wave cut into KV shares;
                          // 9: schedule 5 (attention5.cuh): persistent CTAs, items overlapped, remainder cut into KV shares
   int gemm_narrow_tiles = 1;  // allow 224-wide tiles where they cut wave quantisation (option "gemm_narrow_tiles")
+  int gemm_k_snake = 0;  // GemmParams::k_snake on the banded wide-K GEMMs: -3 .. -6 GB of DRAM traffic per cfg3 step, -0.3 .. -0.5 % step time, but a
+                         // row's fp32 summation order then depends on where its tile sits, i.e. on the batch it is in -- off by default (profiles/r2h_band.md)
   int gemm_m_band = -1;  // tile order of the wide-K GEMMs (ff down, single proj_out), whose A operand outgrows the L2 at N >= 4608:
                          // 0 = M-fastest over all M tiles, b > 0 = bands of b M tiles (GemmParams::m_band), -1 = per shape (band_for)
   int gemm_l2_hints = 0;  // bit 0: A (activation) loads evict_last, bit 1: B (weight) loads evict_first (option "gemm_l2_hints")
@@ -1006,6 +1008,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
         p.g[g].gate = mod + mod_double(i, g == 0, 5); p.g[g].gate_stride = mod_rows;
       }
       p.m_band = band_for(rt + ri, 4LL * D, D, bn_d);
+      p.k_snake = (p.m_band != 0) ? gemm_k_snake : 0;
       gemm(c, bn_d, A_MLP, name("d%d.ff2_c", i, ".w"), name("d%d.ff2_x", i, ".w"), p);
     }
   }
@@ -1041,6 +1044,7 @@ void tfx_model::enqueue_forward(const LaunchCtx& c, bool fused_euler, bool want_
       }
       const std::string wn = name("s%d.out", j, ".w");
       p.m_band = band_for(rt + ri, 5LL * D, D, bn_d);
+      p.k_snake = (p.m_band != 0) ? gemm_k_snake : 0;
       gemm(c, bn_d, A_CAT, wn, wn, p);
     }
   }
@@ -1189,9 +1193,14 @@ int tfx_set_option(tfx_handle h, const char* key, int64_t value) {
     h->attn_emu = (int)value;
   } else if (k == "gemm_narrow_tiles") {
     h->gemm_narrow_tiles = value != 0;  // weight-side descriptors are keyed by tile width: nothing to rebuild
+  } else if (k == "gemm_k_snake") {
+    REQUIRE(value == 0 || value == 1, TFX_ERR_INVALID, "gemm_k_snake must be 0 or 1");
+    h->gemm_k_snake = (int)value;
+    h->drop_graphs();
   } else if (k == "gemm_m_band") {
     REQUIRE(value >= -164 && value <= 64, TFX_ERR_INVALID, "gemm_m_band must be -1 (per shape), 0..64 (M bands) or -100 - n (N bands of n tiles)");
     h->gemm_m_band = (int)value;
+    h->drop_graphs();
   } else if (k == "gemm_l2_hints") {
     REQUIRE(value >= 0 && value <= 3, TFX_ERR_INVALID, "gemm_l2_hints must be 0..3");
     h->gemm_l2_hints = (int)value;
@@ -1582,7 +1591,9 @@ int tfx_op_linear_lora(const void* A, int64_t lda, const void* Wt, const void* b
     CUtensorMap mb = make_map_2d(err_, Wt, N, K, K, bn / cg);
     GemmParams p;
     memset(&p, 0, sizeof p);
-    p.N = N; p.K = K; p.num_groups = 1; p.n_split = N; p.mode0 = mode; p.mode1 = mode; p.m_band = m_band;
+    p.N = N; p.K = K; p.num_groups = 1; p.n_split = N; p.mode0 = mode; p.mode1 = mode;
+    p.k_snake = m_band >= 1000 || m_band <= -1000;  // b +- 1000: band b with the k direction alternating per band (GemmParams::k_snake)
+    p.m_band = m_band >= 1000 ? m_band - 1000 : m_band <= -1000 ? m_band + 1000 : m_band;
     p.g[0].M = M; p.g[0].rows_per_sample = M; p.g[0].bias = reinterpret_cast<const bf16*>(bias);
     p.g[0].out = reinterpret_cast<bf16*>(out); p.g[0].ldo = ldo;
     p.g[0].res = reinterpret_cast<const bf16*>(res); p.g[0].ldr = ldo;

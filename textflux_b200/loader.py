@@ -278,10 +278,8 @@ def load_components(root: str, device="cuda", lora: Optional[str] = None, lora_s
     sc = os.path.join(sub("scheduler"), "scheduler_config.json")
     if os.path.exists(sc):
         from .engine import B200FlowMatchEulerScheduler, B200StochasticRFOvershotScheduler
-        import inspect
         with open(sc) as f:
             raw = json.load(f)
-        known = set(inspect.signature(B200FlowMatchEulerScheduler.__init__).parameters) - {"self"}
         cls = B200StochasticRFOvershotScheduler if "Overshot" in raw.get("_class_name", "") else B200FlowMatchEulerScheduler
-        out["scheduler"] = cls(**{k: v for k, v in raw.items() if k in known})
+        out["scheduler"] = cls.from_config(raw)  # refuses the sigma options the FLUX path never sets
     return out

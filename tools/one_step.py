@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--attn-variant", type=int, default=-1)
     ap.add_argument("--m-band", type=int, default=-1)
+    ap.add_argument("--k-snake", type=int, default=-1)
     args = ap.parse_args()
     from textflux_b200 import B200FluxTransformer, synthetic_getter
     from textflux_b200.engine import FrozenConfig
@@ -27,6 +28,8 @@ def main():
     eng = B200FluxTransformer(cfg, synthetic_getter(cfg, 1234, dev), device=dev)
     if args.attn_variant >= 0:
         eng.set_option("attn_variant", args.attn_variant)
+    if args.k_snake >= 0:
+        eng.set_option("gemm_k_snake", args.k_snake)
     if args.m_band >= 0 or args.m_band <= -100:
         eng.set_option("gemm_m_band", args.m_band)
     inp = bench.Inputs(args.workload, dev, 0, 1)
