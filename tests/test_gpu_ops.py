@@ -300,9 +300,12 @@ def _attention(lib, q, k, v, T, q_tiles):
     return torch.cat([txt, img], dim=1)
 
 
-@pytest.mark.parametrize("q_tiles", [5, 25, 6, 26, 36, 46, 9, 29, 49, 7, 27, 37, 47],
+_EXTRA_QT = [int(x) for x in os.environ.get("TFX_EXTRA_QT", "").split(",") if x]  # experiment builds (tools/experiments): extra schedule codes
+
+
+@pytest.mark.parametrize("q_tiles", [5, 25, 6, 26, 36, 46, 9, 29, 49, 7, 27, 37, 47] + _EXTRA_QT,
                          ids=["s3", "s3_e2", "s3split", "s3split_e2", "s3split_e3", "s3split_e4", "stream", "stream_e2", "stream_e4",
-                              "persist", "persist_e2", "persist_e3", "persist_e4"])
+                              "persist", "persist_e2", "persist_e3", "persist_e4"] + [f"extra{x}" for x in _EXTRA_QT])
 @pytest.mark.parametrize("B,H,T,S,dh", [(1, 2, 128, 128, 128), (1, 24, 512, 2048, 128), (2, 4, 16, 64, 64), (1, 3, 40, 217, 128),
                                           (2, 2, 100, 412, 64), (1, 1, 0, 128, 128), (1, 2, 0, 64, 128), (1, 2, 7, 30, 64),
                                           (1, 2, 512, 4608, 128), (1, 24, 512, 4608, 128), (3, 5, 77, 1500, 128), (1, 150, 0, 300, 64),
@@ -320,7 +323,7 @@ def test_attention(lib, B, H, T, S, dh, q_tiles):
     assert err < 8e-3, err
 
 
-@pytest.mark.parametrize("q_tiles", [26, 27, 29], ids=["s3split", "persist", "stream"])
+@pytest.mark.parametrize("q_tiles", [26, 27, 29] + _EXTRA_QT, ids=["s3split", "persist", "stream"] + [f"extra{x}" for x in _EXTRA_QT])
 @pytest.mark.parametrize("kind", ["jump", "ramp", "first_tile_peak"])
 def test_attention_on_adversarial_scores(lib, q_tiles, kind):
     """The lazily rescaled running maximum (attn_softmax_tile: the reference only moves when the true maximum ran away by more than

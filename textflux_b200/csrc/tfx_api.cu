@@ -19,6 +19,9 @@
 #include "attention3.cuh"
 #include "attention4.cuh"
 #include "attention5.cuh"
+#ifdef TFX_ATTN8
+#include "../../tools/experiments/attention8.cuh"
+#endif
 #include "conditioning.cuh"
 #include "gemm.cuh"
 #include "pointwise.cuh"
@@ -240,6 +243,12 @@ void configure_kernels(std::string* err_) {
   CUDA_TRY(cudaFuncSetAttribute(attention5_tcgen05_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn3Cfg<128>::kSmemBytes));
   TFX_ATTN5_ATTR(128, 0); TFX_ATTN5_ATTR(128, 2); TFX_ATTN5_ATTR(128, 3); TFX_ATTN5_ATTR(128, 4); TFX_ATTN5_ATTR(64, 0); TFX_ATTN5_ATTR(64, 2);
 #undef TFX_ATTN5_ATTR
+#ifdef TFX_ATTN8
+  CUDA_TRY(cudaFuncSetAttribute(attention8_tcgen05_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn8Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention8_tcgen05_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn8Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention8_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn8Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention8_tcgen05_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn8Cfg<64>::kSmemBytes));
+#endif
   CUDA_TRY(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   done = true;
 }
@@ -524,6 +533,26 @@ void launch_attention5(const LaunchCtx& c, int head_dim, int emu, const CUtensor
   CUDA_TRY(cudaGetLastError());
   ++*c.counter;
 }
+
+#ifdef TFX_ATTN8
+void launch_attention8(const LaunchCtx& c, int head_dim, int emu, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnParams& p) {
+  std::string* err_ = c.err_;
+  ProfScope ps(c, KF_ATTN);
+  dim3 grid((p.N + 255) / 256, p.H, p.B);
+  if (head_dim == 64) {
+    CUDA_TRY(launch_ex(attention8_tcgen05_kernel<64, 2>, grid, dim3(Attn8Cfg<64>::kThreads), Attn8Cfg<64>::kSmemBytes, c, 1, tq, tk, tv, p));
+  } else if (emu == 0) {
+    CUDA_TRY(launch_ex(attention8_tcgen05_kernel<128, 0>, grid, dim3(Attn8Cfg<128>::kThreads), Attn8Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
+  } else if (emu == 3) {
+    CUDA_TRY(launch_ex(attention8_tcgen05_kernel<128, 3>, grid, dim3(Attn8Cfg<128>::kThreads), Attn8Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
+  } else {
+    CUDA_TRY(launch_ex(attention8_tcgen05_kernel<128, 2>, grid, dim3(Attn8Cfg<128>::kThreads), Attn8Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
+  }
+  CUDA_TRY(cudaGetLastError());
+  ++*c.counter;
+}
+#endif
 
 // attn_variant 0 ("auto"): schedule 5 where its work decomposition pays, schedule 3 elsewhere.  Measured (tools/bench_kernels.py,
 // profiles/r2e_kernels_attn.json, 24 heads, TFLOP/s, schedule 3 / schedule 5): N = 2560 936 / 865, 4608 1287 / 1249, 5120 1131 /
@@ -1736,6 +1765,10 @@ int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int
       p.trace = reinterpret_cast<long long*>(g_attn_trace);
       p.cta_trace = reinterpret_cast<long long*>(g_attn_cta_trace);
       launch_attention3(c, head_dim, emu, sched == 6, trace_build, mq, mk, mv, p);
+#ifdef TFX_ATTN8
+    } else if (sched == 8) {
+      launch_attention8(c, head_dim, emu, mq, mk, mv, p);
+#endif
     } else {
       REQUIRE(false, TFX_ERR_INVALID, "attention schedule code %d unknown (5 | 6 | 7 | 9, + 10 * emu)", q_tiles);
     }

@@ -114,7 +114,7 @@ def main():
         out = torch.empty(N, H * dh, device="cuda", dtype=torch.bfloat16)
         row = {"kernel": "attention", "N": N, "H": H, "dh": dh}
         fl = 4.0 * N * N * H * dh
-        for qt in (26, 29, 27, 7, 37):
+        for qt in [26, 29, 27, 7, 37] + [int(x) for x in os.environ.get("TFX_EXTRA_QT", "").split(",") if x]:
             def f():
                 _lib.check(lib.tfx_op_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), H * dh, 1, H, T, S, dh, qt, st))
             ms = timeit(f, flush=flush)
