@@ -22,6 +22,15 @@
 #ifdef TFX_ATTN8
 #include "../../tools/experiments/attention8.cuh"
 #endif
+#ifdef TFX_ATTN9
+#include "../../tools/experiments/attention9.cuh"
+#endif
+#ifdef TFX_ATTN10
+#include "../../tools/experiments/attention10.cuh"
+#endif
+#ifdef TFX_ATTN11
+#include "../../tools/experiments/attention11.cuh"
+#endif
 #include "conditioning.cuh"
 #include "gemm.cuh"
 #include "pointwise.cuh"
@@ -248,6 +257,26 @@ void configure_kernels(std::string* err_) {
   CUDA_TRY(cudaFuncSetAttribute(attention8_tcgen05_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn8Cfg<128>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention8_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn8Cfg<128>::kSmemBytes));
   CUDA_TRY(cudaFuncSetAttribute(attention8_tcgen05_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn8Cfg<64>::kSmemBytes));
+#endif
+#ifdef TFX_ATTN9
+  CUDA_TRY(cudaFuncSetAttribute(attention9_tcgen05_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn9Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention9_tcgen05_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn9Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention9_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn9Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention9_tcgen05_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn9Cfg<64>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention9_tcgen05_kernel<128, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn9Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention9_tcgen05_kernel<128, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn9Cfg<128>::kSmemBytes));
+#endif
+#ifdef TFX_ATTN10
+  CUDA_TRY(cudaFuncSetAttribute(attention10_tcgen05_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn10Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention10_tcgen05_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn10Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention10_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn10Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention10_tcgen05_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn10Cfg<64>::kSmemBytes));
+#endif
+#ifdef TFX_ATTN11
+  CUDA_TRY(cudaFuncSetAttribute(attention11_tcgen05_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn11Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention11_tcgen05_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn11Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention11_tcgen05_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn11Cfg<128>::kSmemBytes));
+  CUDA_TRY(cudaFuncSetAttribute(attention11_tcgen05_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn11Cfg<128>::kSmemBytes));
 #endif
   CUDA_TRY(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   done = true;
@@ -549,6 +578,72 @@ void launch_attention8(const LaunchCtx& c, int head_dim, int emu, const CUtensor
   } else {
     CUDA_TRY(launch_ex(attention8_tcgen05_kernel<128, 2>, grid, dim3(Attn8Cfg<128>::kThreads), Attn8Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
   }
+  CUDA_TRY(cudaGetLastError());
+  ++*c.counter;
+}
+#endif
+
+#ifdef TFX_ATTN9
+void launch_attention9(const LaunchCtx& c, int head_dim, int emu, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnParams& p) {
+  std::string* err_ = c.err_;
+  ProfScope ps(c, KF_ATTN);
+  dim3 grid((p.N + 127) / 128, p.H, p.B);
+  if (head_dim == 64) {
+    CUDA_TRY(launch_ex(attention9_tcgen05_kernel<64, 2>, grid, dim3(Attn9Cfg<64>::kThreads), Attn9Cfg<64>::kSmemBytes, c, 1, tq, tk, tv, p));
+  } else if (emu == 0) {
+    CUDA_TRY(launch_ex(attention9_tcgen05_kernel<128, 0>, grid, dim3(Attn9Cfg<128>::kThreads), Attn9Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
+  } else if (emu == 1 && p.trace) {
+    CUDA_TRY(launch_ex(attention9_tcgen05_kernel<128, 2, true, true>, grid, dim3(Attn9Cfg<128>::kThreads), Attn9Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
+  } else if (emu == 1) {  // experiment: emu code 1 = split-issue variant at emu 2
+    CUDA_TRY(launch_ex(attention9_tcgen05_kernel<128, 2, true>, grid, dim3(Attn9Cfg<128>::kThreads), Attn9Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
+  } else if (emu == 3) {
+    CUDA_TRY(launch_ex(attention9_tcgen05_kernel<128, 3>, grid, dim3(Attn9Cfg<128>::kThreads), Attn9Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
+  } else {
+    CUDA_TRY(launch_ex(attention9_tcgen05_kernel<128, 2>, grid, dim3(Attn9Cfg<128>::kThreads), Attn9Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
+  }
+  CUDA_TRY(cudaGetLastError());
+  ++*c.counter;
+}
+#endif
+
+#ifdef TFX_ATTN10
+void launch_attention10(const LaunchCtx& c, int head_dim, int emu, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                        const AttnParams& p) {
+  std::string* err_ = c.err_;
+  ProfScope ps(c, KF_ATTN);
+  dim3 grid((p.N + 127) / 128, p.H, p.B);
+  if (head_dim == 64) {
+    CUDA_TRY(launch_ex(attention10_tcgen05_kernel<64, 2>, grid, dim3(Attn10Cfg<64>::kThreads), Attn10Cfg<64>::kSmemBytes, c, 1, tq, tk, tv, p));
+  } else if (emu == 0) {
+    CUDA_TRY(launch_ex(attention10_tcgen05_kernel<128, 0>, grid, dim3(Attn10Cfg<128>::kThreads), Attn10Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
+  } else if (emu == 3) {
+    CUDA_TRY(launch_ex(attention10_tcgen05_kernel<128, 3>, grid, dim3(Attn10Cfg<128>::kThreads), Attn10Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
+  } else {
+    CUDA_TRY(launch_ex(attention10_tcgen05_kernel<128, 2>, grid, dim3(Attn10Cfg<128>::kThreads), Attn10Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p));
+  }
+  CUDA_TRY(cudaGetLastError());
+  ++*c.counter;
+}
+#endif
+
+#ifdef TFX_ATTN11
+void launch_attention11(const LaunchCtx& c, int head_dim, int emu, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                        const AttnParams& p) {
+  std::string* err_ = c.err_;
+#ifdef TFX_ATTN9
+  if (head_dim != 128) return launch_attention9(c, head_dim, emu, tq, tk, tv, p);
+#endif
+  REQUIRE(head_dim == 128, TFX_ERR_INVALID, "schedule 11 (experiment) is built for head_dim 128 only");
+  ProfScope ps(c, KF_ATTN);
+  dim3 grid((p.N + 127) / 128, p.H, p.B);
+#define TFX_ATTN11_L(EMU) \
+  CUDA_TRY(launch_ex(attention11_tcgen05_kernel<128, EMU>, grid, dim3(Attn11Cfg<128>::kThreads), Attn11Cfg<128>::kSmemBytes, c, 1, tq, tk, tv, p))
+  if (emu == 0) TFX_ATTN11_L(0);
+  else if (emu == 3) TFX_ATTN11_L(3);
+  else if (emu == 4) TFX_ATTN11_L(4);
+  else TFX_ATTN11_L(2);
+#undef TFX_ATTN11_L
   CUDA_TRY(cudaGetLastError());
   ++*c.counter;
 }
@@ -1768,6 +1863,19 @@ int tfx_op_attention(const void* q, const void* k, const void* v, void* out, int
 #ifdef TFX_ATTN8
     } else if (sched == 8) {
       launch_attention8(c, head_dim, emu, mq, mk, mv, p);
+#endif
+#ifdef TFX_ATTN11
+    } else if (sched == 2) {
+      launch_attention11(c, head_dim, emu, mq, mk, mv, p);
+#endif
+#ifdef TFX_ATTN10
+    } else if (sched == 3) {
+      launch_attention10(c, head_dim, emu, mq, mk, mv, p);
+#endif
+#ifdef TFX_ATTN9
+    } else if (sched == 4) {
+      if (trace_build) p.trace = reinterpret_cast<long long*>(g_attn_trace);
+      launch_attention9(c, head_dim, emu, mq, mk, mv, p);
 #endif
     } else {
       REQUIRE(false, TFX_ERR_INVALID, "attention schedule code %d unknown (5 | 6 | 7 | 9, + 10 * emu)", q_tiles);
