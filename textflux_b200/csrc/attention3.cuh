@@ -69,7 +69,8 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* s_full = v_empty + kVS;      // [2]
   uint64_t* p_full = s_full + 2;         // [2 q][2 halves]
   uint64_t* pv_done = p_full + 4;        // [2]
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* h0_done = pv_done + 2;       // [2]  kAttnNoMax: the PV MMAs over keys 0..63 of the tile have retired
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(h0_done + 2);
   constexpr bool kTwoBars = kSplitP;
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
@@ -104,6 +105,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       mbar_init(&p_full[2 * i], 4);
       mbar_init(&p_full[2 * i + 1], 4);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&h0_done[i], 1);
     }
     fence_mbar_init();
   }
@@ -200,6 +202,7 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           if (tracing && leader) p.trace[(j * 2 + q) * kAttnTraceSlots + 5] = clock64();
           if (kTwoBars) {
             issue_pv(q, vs, 0, 4, j == 0);
+            if (kAttnNoMax && leader) umma_commit(&h0_done[q]);
             mbar_wait(&p_full[2 * q + 1], j & 1);
             tc_fence_after();
             issue_pv(q, vs, 4, 8, false);
@@ -256,7 +259,11 @@ attention3_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         auto stamp = [&](int slot) {
           if (tr) p.trace[(j * 2 + q) * kAttnTraceSlots + slot] = clock64();
         };
-        attn_softmax_tile<kHeadDim, kEmu>(t_s, t_o, c, valid, j == 0, m, l, pend, handover, stamp);
+        auto wait_h0 = [&]() {
+          mbar_wait(&h0_done[q], j & 1);
+          tc_fence_after();
+        };
+        attn_softmax_tile<kHeadDim, kEmu, kSplitP>(t_s, t_o, c, valid, j == 0, m, l, pend, handover, stamp, wait_h0);
       }
       // ---- finalize: O / l -> bf16, token-major store
       if (kTrace && ctr && warp == 4 && lane == 0) ctr[4] = (long long)globaltimer_ns();

@@ -114,7 +114,8 @@ attention4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* s_full = v_empty + kVS;      // [2]
   uint64_t* p_full = s_full + 2;         // [2 q][2 halves]
   uint64_t* pv_done = p_full + 4;        // [2]
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* h0_done = pv_done + 2;       // [2]  kAttnNoMax: the PV MMAs over keys 0..63 of the tile have retired
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(h0_done + 2);
   int* last_flag = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
@@ -133,6 +134,7 @@ attention4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       mbar_init(&p_full[2 * i], 4);
       mbar_init(&p_full[2 * i + 1], 4);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&h0_done[i], 1);
     }
     fence_mbar_init();
   }
@@ -224,6 +226,7 @@ attention4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           mbar_wait(&p_full[2 * q], jj & 1);
           tc_fence_after();
           issue_pv(q, vs, 0, 4, jj == 0);
+          if (kAttnNoMax && leader) umma_commit(&h0_done[q]);
           mbar_wait(&p_full[2 * q + 1], jj & 1);
           tc_fence_after();
           issue_pv(q, vs, 4, 8, false);
@@ -266,7 +269,11 @@ attention4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[2 * q + half]);
       };
-      attn_softmax_tile<kHeadDim, kEmu>(t_s, t_o, c, valid, jj == 0, m, l, pend, handover, [](int) {});
+      auto wait_h0 = [&]() {
+        mbar_wait(&h0_done[q], jj & 1);
+        tc_fence_after();
+      };
+      attn_softmax_tile<kHeadDim, kEmu, true>(t_s, t_o, c, valid, jj == 0, m, l, pend, handover, [](int) {}, wait_h0);
     }
     mbar_wait(&pv_done[q], (n_it - 1) & 1);
     tc_fence_after();

@@ -115,7 +115,8 @@ attention5_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   uint64_t* p_full = s_full + 2;         // [2 q][2 halves]
   uint64_t* pv_done = p_full + 4;        // [2]  once per KV iteration
   uint64_t* o_free = pv_done + 2;        // [2]  once per item: O_q has been pulled into registers
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(o_free + 2);
+  uint64_t* h0_done = o_free + 2;        // [2]  kAttnNoMax: the PV MMAs over keys 0..63 of the tile have retired
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(h0_done + 2);
   int* last_flag = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(bars) + 256);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
@@ -136,6 +137,7 @@ attention5_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       mbar_init(&p_full[2 * i + 1], 4);
       mbar_init(&pv_done[i], 1);
       mbar_init(&o_free[i], 4);
+      mbar_init(&h0_done[i], 1);
     }
     fence_mbar_init();
   }
@@ -248,6 +250,7 @@ attention5_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
             tc_fence_after();
             if (kTrace && ctr && leader && jj == 0 && q == 0 && k < 8) ctr[k * 8 + 5] = (long long)globaltimer_ns();
             issue_pv(q, vs, 0, 4, jj == 0);
+            if (kAttnNoMax && leader) umma_commit(&h0_done[q]);
             mbar_wait(&p_full[2 * q + 1], g & 1);
             tc_fence_after();
             issue_pv(q, vs, 4, 8, false);
@@ -305,7 +308,11 @@ attention5_tcgen05_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[2 * q + half]);
         };
-        attn_softmax_tile<kHeadDim, kEmu>(t_s, t_o, c, valid, jj == 0, m, l, pend, handover, [](int) {});
+        auto wait_h0 = [&]() {
+          mbar_wait(&h0_done[q], g & 1);
+          tc_fence_after();
+        };
+        attn_softmax_tile<kHeadDim, kEmu, true>(t_s, t_o, c, valid, jj == 0, m, l, pend, handover, [](int) {}, wait_h0);
       }
       // ---- end of item: the last PV has to retire, then O_q leaves TMEM so that the next item's first PV may overwrite it
       if (kTrace && ctr && warp == 4 && lane == 0 && k < 8) ctr[k * 8 + 1] = (long long)globaltimer_ns();

@@ -166,10 +166,99 @@ __device__ __forceinline__ void attn_load_scores(uint32_t t_s, int valid, uint32
 #endif
 constexpr bool kAttnLag = TFX_ATTN_LAG != 0;
 
-template <int kHeadDim, int kEmu, typename Handover, typename Stamp>
+// kAttnNoMax (-DTFX_ATTN_NOMAX=1): after a row's first tile NO maximum is computed.  The reference m stays where it is and the
+//   probabilities are evaluated against it directly; what the maximum protected against -- probabilities running away from the
+//   reference -- is detected on the half-row sums that are computed anyway (sum of 64 probabilities > 2^16, or inf / NaN), before the
+//   half is handed over.  A flagged first half falls back to the exact path (nothing handed over yet, scores in registers); a flagged
+//   second half waits for the PV MMAs of the first half (`wait_h0`, a commit the issuer makes per tile), moves the reference, rescales
+//   O and l and re-evaluates its 64 columns.  Saves the 98 FMNMX per warp and tile and takes the maximum off the S-ready -> P path.
+#ifndef TFX_ATTN_NOMAX
+#define TFX_ATTN_NOMAX 0
+#endif
+constexpr bool kAttnNoMax = TFX_ATTN_NOMAX != 0;
+constexpr float kAttnSumLimit = 65536.0f;
+
+__device__ __forceinline__ float attn_half_max(const uint32_t (&a)[32], const uint32_t (&b)[32]) {
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    mx0 = fmaxf(mx0, __uint_as_float(a[i]));
+    mx1 = fmaxf(mx1, __uint_as_float(b[i]));
+  }
+  return fmaxf(mx0, mx1);
+}
+
+template <int kHeadDim, int kEmu, bool kSplit, typename Handover, typename Stamp, typename WaitH0>
 __device__ __forceinline__ void attn_softmax_tile(uint32_t t_s, uint32_t t_o, float c, int valid, bool first, float& m, float& l,
-                                                  float& pend, Handover&& handover, Stamp&& stamp) {
+                                                  float& pend, Handover&& handover, Stamp&& stamp, WaitH0&& wait_h0) {
   const f32x2 c2 = pack2(c, c);
+  if (kAttnNoMax && kSplit && !kAttnLag) {  // whole-P hand-over keeps the exact path: its first half is not consumed early
+    uint32_t sr[4][32];
+    attn_load_scores(t_s, valid, sr);
+    stamp(1);
+    uint32_t pk[32];
+    if (!first) {
+      const float mc = m * c;
+      const f32x2 nmc2 = pack2(-mc, -mc);
+      f32x2 sum2 = pack2(0.f, 0.f);
+      attn_exp_half<kEmu>(sr[0], sr[1], c2, nmc2, sum2, pk);
+      float a0, a1;
+      unpack2(sum2, a0, a1);
+      const float s_a = a0 + a1;
+      stamp(2);
+      if (!__any_sync(0xffffffffu, !(s_a <= kAttnSumLimit))) {
+        handover(0, pk);
+        stamp(3);
+        sum2 = pack2(0.f, 0.f);
+        attn_exp_half<kEmu>(sr[2], sr[3], c2, nmc2, sum2, pk);
+        unpack2(sum2, a0, a1);
+        float s_b = a0 + a1;
+        const bool over = !(s_b <= kAttnSumLimit);
+        if (__any_sync(0xffffffffu, over)) {
+          // second half ran away after the first was handed over: O holds PV(0..j-1) + PV over keys 0..63 of this tile once wait_h0 returns
+          const float m_new = over ? fmaxf(attn_half_max(sr[2], sr[3]), m) : m;
+          const float alpha = ex2((m - m_new) * c);
+          wait_h0();
+          attn_rescale_o<kHeadDim>(t_o, alpha);
+          l = (l + s_a) * alpha;
+          m = m_new;
+          const float mc1 = m * c;
+          sum2 = pack2(0.f, 0.f);
+          attn_exp_half<kEmu>(sr[2], sr[3], c2, pack2(-mc1, -mc1), sum2, pk);
+          unpack2(sum2, a0, a1);
+          l += a0 + a1;
+        } else {
+          l += s_a + s_b;
+        }
+        handover(1, pk);
+        stamp(4);
+        pend = m;
+        return;
+      }
+      // first half ran away: nothing handed over yet -> exact path on the scores in registers
+    }
+    const float mx = attn_row_max(sr);
+    const bool need = (mx - m) * c > kAttnRescaleThreshold;  // true on the first tile (m = -inf)
+    const float m_new = need ? mx : m;
+    const float alpha = need ? ex2((m - m_new) * c) : 1.0f;
+    if (!first && __any_sync(0xffffffffu, need)) attn_rescale_o<kHeadDim>(t_o, alpha);
+    stamp(2);
+    const float mc = m_new * c;
+    const f32x2 nmc2 = pack2(-mc, -mc);
+    f32x2 sum2 = pack2(0.f, 0.f);
+    attn_exp_half<kEmu>(sr[0], sr[1], c2, nmc2, sum2, pk);
+    handover(0, pk);
+    stamp(3);
+    attn_exp_half<kEmu>(sr[2], sr[3], c2, nmc2, sum2, pk);
+    handover(1, pk);
+    stamp(4);
+    float sum0, sum1;
+    unpack2(sum2, sum0, sum1);
+    l = l * alpha + (sum0 + sum1);
+    m = m_new;
+    pend = mx;
+    return;
+  }
   if (kAttnLag && !first) {
     // ---- fast path: reference from the previous tile's maximum; this tile's maximum rides along with the exponentials
     const bool need = (pend - m) * c > kAttnRescaleThreshold;
