@@ -144,13 +144,18 @@ int tfx_textenc_create(const tfx_textenc_config* cfg, int32_t device, tfx_texten
     tfx_textenc* m = new tfx_textenc();
     m->cfg = *cfg;
     m->device = device;
-    cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
-    const size_t n = (size_t)std::max(std::max(3 * m->inner(), cfg->d_ff), cfg->d_model);
-    std::vector<bf16> one(n, __float2bfloat16(1.0f));
-    cudaMalloc(reinterpret_cast<void**>(&m->ones), n * 2);
-    cudaMalloc(reinterpret_cast<void**>(&m->zeros), n * 2);
-    cudaMemcpy(m->ones, one.data(), n * 2, cudaMemcpyHostToDevice);
-    cudaMemset(m->zeros, 0, n * 2);
+    try {
+      CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+      const size_t n = (size_t)std::max(std::max(3 * m->inner(), cfg->d_ff), cfg->d_model);
+      std::vector<bf16> one(n, __float2bfloat16(1.0f));
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->ones), n * 2));
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->zeros), n * 2));
+      CUDA_TRY(cudaMemcpy(m->ones, one.data(), n * 2, cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemset(m->zeros, 0, n * 2));
+    } catch (...) {
+      tfx_textenc_destroy(m);  // frees whatever was allocated before the failure
+      throw;
+    }
     *out = m;
   } catch (const Fail& f) {
     return f.code;
@@ -161,11 +166,11 @@ int tfx_textenc_create(const tfx_textenc_config* cfg, int32_t device, tfx_texten
 void tfx_textenc_destroy(tfx_textenc_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   h->release();
   cudaFree(h->ones);
   cudaFree(h->zeros);
-  cudaStreamDestroy(h->stream);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
 

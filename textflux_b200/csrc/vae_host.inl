@@ -345,14 +345,19 @@ int tfx_vae_create(const tfx_vae_config* cfg, int32_t device, tfx_vae_handle* ou
     tfx_vae* m = new tfx_vae();
     m->cfg = *cfg;
     m->device = device;
-    cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
-    std::vector<bf16> one(2048, __float2bfloat16(1.0f));
-    cudaMalloc(reinterpret_cast<void**>(&m->ones), 4096);
-    cudaMalloc(reinterpret_cast<void**>(&m->zeros), 4096);
-    cudaMemcpy(m->ones, one.data(), 4096, cudaMemcpyHostToDevice);
-    cudaMemset(m->zeros, 0, 4096);
-    cudaMalloc(reinterpret_cast<void**>(&m->gn_partial), (size_t)(1 << 20) * 4);
-    cudaMalloc(reinterpret_cast<void**>(&m->gn_stats), 8192 * 4);
+    try {
+      CUDA_TRY(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+      std::vector<bf16> one(2048, __float2bfloat16(1.0f));
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->ones), 4096));
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->zeros), 4096));
+      CUDA_TRY(cudaMemcpy(m->ones, one.data(), 4096, cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMemset(m->zeros, 0, 4096));
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->gn_partial), (size_t)(1 << 20) * 4));
+      CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&m->gn_stats), 8192 * 4));
+    } catch (...) {
+      tfx_vae_destroy(m);  // frees whatever was allocated before the failure
+      throw;
+    }
     *out = m;
   } catch (const Fail& f) {
     return f.code;
@@ -363,11 +368,11 @@ int tfx_vae_create(const tfx_vae_config* cfg, int32_t device, tfx_vae_handle* ou
 void tfx_vae_destroy(tfx_vae_handle h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   h->release();
   for (void* p : {(void*)h->ones, (void*)h->zeros, (void*)h->gn_partial, (void*)h->gn_stats, (void*)h->zeros_big})
     if (p) cudaFree(p);
-  cudaStreamDestroy(h->stream);
+  if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
 
