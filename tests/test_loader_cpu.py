@@ -173,3 +173,24 @@ def test_checkpoint_resolves_transformers_file_names(tmp_path):
         ld.Checkpoint(str(empty))
     with pytest.raises(ValueError, match="config"):
         ld.load_text_encoder(str(two))  # weights but no config.json: refused before any device work
+
+
+def test_load_components_scheduler_only_directory(tmp_path):
+    """A pipeline directory without model sub-directories yields just the scheduler, built through from_config (which refuses the
+    sigma options the FLUX path never sets) -- no device is touched."""
+    import json
+    from textflux_b200 import B200FlowMatchEulerScheduler, B200StochasticRFOvershotScheduler
+    from textflux_b200 import loader as ld
+    (tmp_path / "scheduler").mkdir()
+    conf = {"_class_name": "FlowMatchEulerDiscreteScheduler", "_diffusers_version": "0.32.0", "shift": 3.0, "use_dynamic_shifting": True,
+            "base_shift": 0.5, "max_shift": 1.15, "base_image_seq_len": 256, "max_image_seq_len": 4096, "num_train_timesteps": 1000,
+            "a_key_from_a_newer_diffusers": None}
+    json.dump(conf, open(tmp_path / "scheduler" / "scheduler_config.json", "w"))
+    parts = ld.load_components(str(tmp_path), device="cpu")
+    assert set(parts) == {"scheduler"} and type(parts["scheduler"]) is B200FlowMatchEulerScheduler
+    assert parts["scheduler"].config["shift"] == 3.0 and parts["scheduler"].config["max_image_seq_len"] == 4096
+    json.dump(dict(conf, _class_name="StochasticRFOvershotDiscreteScheduler"), open(tmp_path / "scheduler" / "scheduler_config.json", "w"))
+    assert type(ld.load_components(str(tmp_path))["scheduler"]) is B200StochasticRFOvershotScheduler
+    json.dump(dict(conf, use_karras_sigmas=True), open(tmp_path / "scheduler" / "scheduler_config.json", "w"))
+    with pytest.raises(ValueError, match="use_karras_sigmas"):
+        ld.load_components(str(tmp_path))
